@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native multi-label EDT.
+
+Metric (BASELINE.json): Mvoxels/s of edtsq on a 512^3 uint32 multi-label volume
+(configs[1]: iid random labels 0..255, anisotropy (1,1,1)), plus the HBM roofline fraction of
+the dominant kernel, plus the same metric end to end from host memory, plus the reference's
+own CPU implementation timed on this box's host cores.
+
+  python bench.py --gpus 1 --steps 20 --warmup 3          # our arm
+  python bench.py --impl reference --steps 2 --warmup 1   # the unmodified reference (CPU)
+  torchrun ... bench.py --gpus N ...                      # one rank per GPU, weak scaling:
+                                                          # each rank owns one 512^3 Z slab
+
+One JSON line on stdout (rank 0).  A "step" is one full transform (X, Y, Z passes) of the
+volume.  Inputs (512 MiB labels + 512 MiB distances) are larger than the 126 MB L2, so no L2
+flush is needed between steps.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+SHAPE = (512, 512, 512)          # x, y, z (x fastest)
+ANISOTROPY = (1.0, 1.0, 1.0)
+LABEL_BYTES = 4
+WORKLOAD = "edtsq 512x512x512 uint32 iid-random labels 0..255, anisotropy (1,1,1), black_border=False (BASELINE.json configs[1])"
+
+
+def make_labels(seed=0, shape=SHAPE):
+  """cfg2 of BASELINE.md section 3: np.asfortranarray(rng(0).integers(0,256,(512,)*3, uint32))."""
+  rng = np.random.default_rng(seed)
+  return np.asfortranarray(rng.integers(0, 256, shape, dtype=np.uint32))
+
+
+def measured_peak_gbs():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  try:
+    with open(path) as fh:
+      return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+  except Exception:
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+  """DRAM bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+  path = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+  try:
+    with open(path) as fh:
+      return json.load(fh)
+  except Exception:
+    return None
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+  QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+           "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+           "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    self.gpu_index = gpu_index
+    self.lines = []
+    self.proc = None
+    self.thread = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+        ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+         "--format=csv,noheader,nounits", "-lms", "200"],
+        stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+      self.proc = None
+      return
+    def pump():
+      for line in self.proc.stdout:
+        self.lines.append(line.strip())
+    self.thread = threading.Thread(target=pump, daemon=True)
+    self.thread.start()
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.25)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    sm, smax, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for line in self.lines:
+      parts = [p.strip() for p in line.split(",")]
+      if len(parts) < 9:
+        continue
+      try:
+        sm.append(float(parts[1])); smax.append(float(parts[2]))
+      except ValueError:
+        continue
+      for name, val in zip(names, parts[5:9]):
+        if val.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm: the unmodified reference (oracle/_ref) on the host cores
+# ---------------------------------------------------------------------------------------
+
+def reference_arm(args):
+  rank, world, _ = dist_env()
+  if rank != 0:
+    return
+  from oracle import oracle
+  ref = oracle.load_reference()
+  kind = "reference"
+  if ref is None:                      # cannot happen where oracle/_ref was built; keep the arm alive
+    ref, kind = oracle, "port"
+  cores = os.cpu_count() or 1
+  labels = make_labels()
+  # bounded sample: a full-x/y Z slab of the workload, deep enough for ~<=8 s per step
+  probe = np.asfortranarray(labels[:, :, :32])
+  t0 = time.perf_counter()
+  ref.edtsq(probe, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
+  rate = probe.size / (time.perf_counter() - t0)            # voxels/s
+  budget_s = max(1.0, min(8.0, 150.0 / max(1, args.steps + args.warmup)))
+  depth = int(min(SHAPE[2], max(32, (rate * budget_s) // (SHAPE[0] * SHAPE[1]) // 32 * 32)))
+  sample = np.asfortranarray(labels[:, :, :depth])
+  for _ in range(args.warmup):
+    ref.edtsq(sample, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    ref.edtsq(sample, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
+  dt = time.perf_counter() - t0
+  mvox = sample.size * args.steps / dt / 1e6
+  sample_desc = "512x512x%d Z slab of the workload per step, parallel=%d threads" % (depth, cores)
+  line = {
+    "impl": "reference", "metric": "Mvoxels/s edtsq 512^3 uint32", "value": mvox, "unit": "Mvoxels/s",
+    "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+    "vs_baseline": None, "dtype": "f32 (f64 envelope internals)", "data": "synthetic",
+    "config": {"workload": WORKLOAD, "sample": sample_desc},
+    "cpu_baseline": {"value": mvox, "unit": "Mvoxels/s", "cores": cores, "kind": kind, "sample": sample_desc},
+    "e2e": {"value": mvox, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    "gpu_launches": 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+
+def cpu_baseline_leg():
+  """The reference's CPU path on this box's host cores, on a bounded sample (rank 0, N=1)."""
+  from oracle import oracle
+  ref = oracle.load_reference()
+  kind = "reference"
+  if ref is None:
+    ref, kind = oracle, "port"
+  cores = (os.cpu_count() or 1) if kind == "reference" else 1
+  labels = make_labels()
+  probe = np.asfortranarray(labels[:, :, :32])
+  t0 = time.perf_counter()
+  ref.edtsq(probe, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
+  rate = probe.size / (time.perf_counter() - t0)
+  depth = int(min(SHAPE[2], max(32, (rate * 15.0) // (SHAPE[0] * SHAPE[1]) // 32 * 32)))
+  sample = np.asfortranarray(labels[:, :, :depth])
+  t0 = time.perf_counter()
+  ref.edtsq(sample, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
+  dt = time.perf_counter() - t0
+  return {"value": sample.size / dt / 1e6, "unit": "Mvoxels/s", "cores": cores, "kind": kind,
+          "sample": "one edtsq of a 512x512x%d Z slab of the workload (%.1f s), parallel=%d" % (depth, dt, cores)}
+
+
+def ours(args):
+  import torch
+  import torch.distributed as dist
+  import edt_b200
+
+  rank, world, local = dist_env()
+  if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  lib = edt_b200._lib()
+  sx, sy, sz = SHAPE
+  nvox = sx * sy * sz
+
+  # every rank owns one 512^3 slab (weak scaling); distinct seeds so ranks do different work
+  labels_np = make_labels(seed=rank)
+  labels_host = torch.from_numpy(np.ascontiguousarray(labels_np.T)).pin_memory()   # memory: x fastest
+  out_host = torch.empty(labels_host.shape, dtype=torch.float32).pin_memory()
+  labels_dev = labels_host.to(dev, non_blocking=True)
+  f_dev = torch.empty(labels_host.shape, dtype=torch.float32, device=dev)
+  torch.cuda.synchronize()
+
+  stream = torch.cuda.current_stream(dev)
+  sptr = ctypes.c_void_p(stream.cuda_stream)
+  lp, fp = labels_dev.data_ptr(), f_dev.data_ptr()
+
+  def check(rc):
+    if rc != 0:
+      raise RuntimeError(lib.edtb200_last_error().decode())
+
+  def step(events=None):
+    if events is not None: events[0].record(stream)
+    check(lib.edtb200_pass_first(lp, LABEL_BYTES, sx, sy, sz, ANISOTROPY[0], 0, 0, fp, local, sptr))
+    if events is not None: events[1].record(stream)
+    check(lib.edtb200_pass_later(lp, LABEL_BYTES, 1, sx, sy, sz, ANISOTROPY[1], 0, 0, 0, fp, local, sptr))
+    if events is not None: events[2].record(stream)
+    check(lib.edtb200_pass_later(lp, LABEL_BYTES, 2, sx, sy, sz, ANISOTROPY[2], 0, 0, 0, fp, local, sptr))
+    if events is not None: events[3].record(stream)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(max(3, args.warmup)):
+    step()
+  barrier()
+
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+  start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  start.record(stream)
+  for k in range(args.steps):
+    step(evs[k])
+  stop.record(stream)
+  barrier()
+  elapsed_ms = start.elapsed_time(stop)
+  clocks = sampler.stop() if rank == 0 else None
+
+  t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  elapsed_ms = float(t.item())
+  ms_per_step = elapsed_ms / args.steps
+  value = nvox * world / (ms_per_step * 1e-3) / 1e6
+
+  # per-pass device times (same timed region) -> roofline of the dominant kernel
+  pass_ms = [statistics.mean(e[i].elapsed_time(e[i + 1]) for e in evs) for i in range(3)]
+  alg_bytes = [(LABEL_BYTES + 4) * nvox, (LABEL_BYTES + 8) * nvox, (LABEL_BYTES + 8) * nvox]
+  names = ["first_axis_kernel<4> (X)", "later_axis_kernel<4> (Y)", "later_axis_kernel<4> (Z)"]
+  dom = max(range(3), key=lambda i: pass_ms[i])
+  peak, peak_src = measured_peak_gbs()
+  achieved = alg_bytes[dom] / (pass_ms[dom] * 1e-3) / 1e9
+  traffic = ncu_traffic()
+  roofline = {
+    "bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+    "frac": achieved / peak, "peak_source": peak_src,
+    "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+    "algorithmic_bytes_per_launch": alg_bytes[dom],
+    "per_pass": [{"kernel": names[i], "ms": pass_ms[i], "algorithmic_bytes": alg_bytes[i],
+                  "GBps": alg_bytes[i] / (pass_ms[i] * 1e-3) / 1e9,
+                  "frac": alg_bytes[i] / (pass_ms[i] * 1e-3) / 1e9 / peak} for i in range(3)],
+    "whole_transform": {"algorithmic_bytes": sum(alg_bytes), "GBps": sum(alg_bytes) / (ms_per_step * 1e-3) / 1e9,
+                        "frac": sum(alg_bytes) / (ms_per_step * 1e-3) / 1e9 / peak},
+  }
+
+  # end to end through the public C-ABI call with HOST buffers (pinned): H2D + passes + D2H
+  e2e_steps = max(2, min(args.steps, 10))
+  hl, ho = labels_host.data_ptr(), out_host.data_ptr()
+  for _ in range(2):
+    check(lib.edtb200_transform(hl, LABEL_BYTES, 3, sx, sy, sz, *ANISOTROPY, 0, 0, ho, local, None))
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    check(lib.edtb200_transform(hl, LABEL_BYTES, 3, sx, sy, sz, *ANISOTROPY, 0, 0, ho, local, None))
+  torch.cuda.synchronize()
+  e2e_s = (time.perf_counter() - t0) / e2e_steps
+  te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+  e2e_s = float(te.item())
+  e2e = {"value": nvox * world / e2e_s / 1e6, "unit": "Mvoxels/s", "ms_per_step": e2e_s * 1e3,
+         "steps": e2e_steps, "h2d_bytes_per_step": nvox * LABEL_BYTES, "d2h_bytes_per_step": nvox * 4,
+         "host_memory": "pinned"}
+
+  # sanity: the device-resident result equals the host-path result
+  same = bool(torch.equal(f_dev.cpu(), out_host))
+
+  if rank == 0:
+    line = {
+      "metric": "Mvoxels/s edtsq 512^3 uint32", "value": value, "unit": "Mvoxels/s",
+      "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f32 (u32 labels)", "data": "synthetic",
+      "config": {"workload": WORKLOAD, "per_gpu": "one 512^3 volume per rank" if world > 1 else "one 512^3 volume",
+                 "l2": "inputs (1 GiB per step) larger than L2; no flush needed",
+                 "timing": "CUDA events on the launch stream, max over ranks"},
+      "roofline": roofline,
+      "e2e": e2e,
+      "gpu_launches": 4 * args.steps,
+      "clocks": clocks,
+      "device_equals_host_path": same,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+      try:
+        line["cpu_baseline"] = cpu_baseline_leg()
+      except Exception as exc:   # the baseline is a report, never the product
+        line["cpu_baseline"] = {"error": repr(exc)}
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  if args.impl == "reference":
+    reference_arm(args)
+  else:
+    ours(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,332 @@
+// edt_capi.cu -- host side of the C ABI declared in include/edt_b200.h.
+//
+// Plays the role of the reference's volume drivers (pyedt::_edt3dsq / _edt2dsq,
+// src/edt.hpp:411-484, 632-678): it owns the pass order X -> Y -> Z over one float32
+// volume that is transformed in place, but the "thread pool" is the CUDA grid and the
+// passes are stream-ordered kernel launches.  No CPU fallback exists in this file.
+#include "../../include/edt_b200.h"
+#include "edt_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess)                                                         \
+      return fail(e__ == cudaErrorMemoryAllocation ? EDTB200_ENOMEM : EDTB200_ECUDA, \
+                  "%s failed: %s", #expr, cudaGetErrorString(e__));                 \
+  } while (0)
+
+constexpr int kMaxDevices = 64;
+
+// Per-device cached state for calls that take host buffers.
+struct DeviceCache {
+  void* labels = nullptr;
+  size_t labels_bytes = 0;
+  float* dist = nullptr;
+  size_t dist_bytes = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  bool probed = false;
+};
+
+std::mutex g_mutex;
+DeviceCache g_cache[kMaxDevices];
+
+int probe(int device, DeviceCache** out) {
+  if (device < 0 || device >= kMaxDevices) return fail(EDTB200_EINVAL, "bad device %d", device);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(EDTB200_ECUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device >= count) return fail(EDTB200_EINVAL, "device %d out of range (%d visible)", device, count);
+  DeviceCache& dc = g_cache[device];
+  CUDA_TRY(cudaSetDevice(device));
+  if (!dc.probed) {
+    CUDA_TRY(cudaDeviceGetAttribute(&dc.sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&dc.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    dc.probed = true;
+  }
+  *out = &dc;
+  return 0;
+}
+
+int check_dims(int label_bytes, int ndim, int64_t& sx, int64_t& sy, int64_t& sz) {
+  if (!(label_bytes == 1 || label_bytes == 2 || label_bytes == 4 || label_bytes == 8))
+    return fail(EDTB200_EINVAL, "label_bytes must be 1, 2, 4 or 8 (got %d)", label_bytes);
+  if (ndim < 1 || ndim > 3) return fail(EDTB200_EINVAL, "ndim must be 1, 2 or 3 (got %d)", ndim);
+  if (ndim < 3) sz = 1;
+  if (ndim < 2) sy = 1;
+  if (sx < 0 || sy < 0 || sz < 0) return fail(EDTB200_EINVAL, "negative size");
+  const int64_t lim = (int64_t)1 << 30;
+  if (sx > lim || sy > lim || sz > lim) return fail(EDTB200_ELIMIT, "axis longer than 2^30");
+  return 0;
+}
+
+// ---- launches ---------------------------------------------------------------------
+
+template <int Bytes>
+int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float w, int border,
+                 int flags, const DeviceCache& dc, cudaStream_t stream) {
+  using namespace edtb200;
+  const int count = (int)sx + 1;
+  float* table = nullptr;
+  CUDA_TRY(cudaMallocAsync(&table, sizeof(float) * (size_t)count, stream));
+  step_table_kernel<<<1, 32, 0, stream>>>(w, count, table);
+  CUDA_TRY(cudaGetLastError());
+
+  const int nwords = (int)(sx >> 5) + 1;
+  const size_t per_warp = sizeof(uint32_t) * 4 * (size_t)nwords;
+  int warps = 8;
+  while (warps > 1 && per_warp * warps > (size_t)dc.max_smem_optin) warps >>= 1;
+  if (per_warp * warps > (size_t)dc.max_smem_optin) {
+    cudaFreeAsync(table, stream);
+    return fail(EDTB200_ELIMIT, "first axis of %lld voxels exceeds the shared-memory line buffer",
+                (long long)sx);
+  }
+  const size_t smem = per_warp * warps;
+  auto kern = first_axis_kernel<Bytes>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = (nlines + warps - 1) / warps;
+  const int64_t cap = (int64_t)dc.sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(
+      static_cast<const typename LabelOf<Bytes>::type*>(labels), f, nlines, (int)sx, table, border, flags);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaFreeAsync(table, stream));
+  return 0;
+}
+
+template <int Bytes>
+int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, float w, int border_lo,
+                 int border_hi, int flags, const DeviceCache& dc, cudaStream_t stream) {
+  using namespace edtb200;
+  using LT = typename LabelOf<Bytes>::type;
+  LineGeom g = g0;
+  const float w2 = w * w;                       // float product, as src/edt.hpp:181
+  const int nchunks = (g.n + 31) >> 5;
+  const size_t smem = (size_t)g.n * 128 + (size_t)nchunks * 256;
+  if (smem <= (size_t)dc.max_smem_optin) {
+    g.tiles_per_outer = (int)((g.inner_count + 31) / 32);
+    const int64_t tiles = (int64_t)g.tiles_per_outer * g.outer_count;
+    if (tiles > 0x7fffffffLL) return fail(EDTB200_ELIMIT, "too many line tiles");
+    int warps = nchunks < 16 ? nchunks : 16;
+    auto kern = later_axis_kernel<Bytes>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(static_cast<const LT*>(labels), f, g, w2,
+                                                        border_lo, border_hi, flags);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  // lines too long for a shared-memory tile: out of place through a temporary volume
+  const int64_t lines = g.inner_count * g.outer_count;
+  const size_t bytes = sizeof(float) * (size_t)lines * (size_t)g.n;
+  float* tmp = nullptr;
+  CUDA_TRY(cudaMallocAsync(&tmp, bytes, stream));
+  const int64_t blocks = (lines + 127) / 128;
+  if (blocks > 0x7fffffffLL) { cudaFreeAsync(tmp, stream); return fail(EDTB200_ELIMIT, "too many lines"); }
+  later_axis_long_kernel<Bytes><<<(unsigned)blocks, 128, 0, stream>>>(
+      static_cast<const LT*>(labels), f, tmp, g, w2, border_lo, border_hi, flags);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(f, tmp, bytes, cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(cudaFreeAsync(tmp, stream));
+  return 0;
+}
+
+int dispatch_first(int label_bytes, const void* labels, float* f, int64_t nlines, int64_t sx, float w,
+                   int border, int flags, const DeviceCache& dc, cudaStream_t s) {
+  switch (label_bytes) {
+    case 1: return launch_first<1>(labels, f, nlines, sx, w, border, flags, dc, s);
+    case 2: return launch_first<2>(labels, f, nlines, sx, w, border, flags, dc, s);
+    case 4: return launch_first<4>(labels, f, nlines, sx, w, border, flags, dc, s);
+    default: return launch_first<8>(labels, f, nlines, sx, w, border, flags, dc, s);
+  }
+}
+
+int dispatch_later(int label_bytes, const void* labels, float* f, const edtb200::LineGeom& g, float w,
+                   int lo, int hi, int flags, const DeviceCache& dc, cudaStream_t s) {
+  switch (label_bytes) {
+    case 1: return launch_later<1>(labels, f, g, w, lo, hi, flags, dc, s);
+    case 2: return launch_later<2>(labels, f, g, w, lo, hi, flags, dc, s);
+    case 4: return launch_later<4>(labels, f, g, w, lo, hi, flags, dc, s);
+    default: return launch_later<8>(labels, f, g, w, lo, hi, flags, dc, s);
+  }
+}
+
+edtb200::LineGeom geom_for_axis(int axis, int64_t sx, int64_t sy, int64_t sz) {
+  edtb200::LineGeom g;
+  if (axis == 1) {
+    g.outer_count = sz; g.outer_stride = sx * sy; g.inner_count = sx; g.line_stride = sx; g.n = (int)sy;
+  } else {
+    g.outer_count = 1; g.outer_stride = 0; g.inner_count = sx * sy; g.line_stride = sx * sy; g.n = (int)sz;
+  }
+  g.tiles_per_outer = 0;
+  return g;
+}
+
+// All passes of one transform on device-resident buffers.
+int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_t sy, int64_t sz,
+               float wx, float wy, float wz, int border, int flags, float* f,
+               const DeviceCache& dc, cudaStream_t stream) {
+  using namespace edtb200;
+  // sqrt / sign are applied by whichever pass is the last one; background-as-label (sdf)
+  // changes the first pass only -- later passes treat every run alike.
+  const int epilogue = ((flags & EDTB200_SQRT) ? kSqrt : 0) | ((flags & EDTB200_SIGNED) ? kNegate : 0);
+  const int zero_label = (flags & EDTB200_SIGNED) ? kZeroLabel : 0;
+  int rc = dispatch_first(label_bytes, labels, f, sy * sz, sx, wx, border,
+                          zero_label | (ndim == 1 ? epilogue : 0), dc, stream);
+  if (rc) return rc;
+  if (ndim >= 2) {
+    rc = dispatch_later(label_bytes, labels, f, geom_for_axis(1, sx, sy, sz), wy, border, border,
+                        ndim == 2 ? epilogue : 0, dc, stream);
+    if (rc) return rc;
+  }
+  if (ndim >= 3) {
+    rc = dispatch_later(label_bytes, labels, f, geom_for_axis(2, sx, sy, sz), wz, border, border,
+                        epilogue, dc, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int edtb200_version(void) { return EDTB200_VERSION; }
+
+const char* edtb200_last_error(void) { return g_error; }
+
+int edtb200_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return count;
+}
+
+int edtb200_transform(const void* labels, int label_bytes, int ndim, int64_t sx, int64_t sy, int64_t sz,
+                      float wx, float wy, float wz, int black_border, int flags, float* out,
+                      int device, void* stream_v) {
+  int rc = check_dims(label_bytes, ndim, sx, sy, sz);
+  if (rc) return rc;
+  const int64_t total = sx * sy * sz;
+  if (total == 0) return 0;
+  if (!labels || !out) return fail(EDTB200_EINVAL, "null pointer");
+
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceCache* dc = nullptr;
+  rc = probe(device, &dc);
+  if (rc) return rc;
+
+  const bool lab_dev = flags & EDTB200_LABELS_ON_DEVICE;
+  const bool out_dev = flags & EDTB200_OUT_ON_DEVICE;
+  const int border = black_border != 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+
+  if (lab_dev && out_dev)
+    return run_passes(labels, label_bytes, ndim, sx, sy, sz, wx, wy, wz, border, flags, out, *dc, stream);
+
+  // host memory involved: stage through cached device buffers, synchronous on return
+  if (!stream) {
+    if (!dc->stream) CUDA_TRY(cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking));
+    stream = dc->stream;
+  }
+  const size_t lab_bytes = (size_t)total * (size_t)label_bytes;
+  const size_t out_bytes = (size_t)total * sizeof(float);
+  const void* d_labels = labels;
+  float* d_out = out;
+  if (!lab_dev) {
+    if (dc->labels_bytes < lab_bytes) {
+      if (dc->labels) cudaFree(dc->labels);
+      dc->labels = nullptr; dc->labels_bytes = 0;
+      CUDA_TRY(cudaMalloc(&dc->labels, lab_bytes));
+      dc->labels_bytes = lab_bytes;
+    }
+    CUDA_TRY(cudaMemcpyAsync(dc->labels, labels, lab_bytes, cudaMemcpyHostToDevice, stream));
+    d_labels = dc->labels;
+  }
+  if (!out_dev) {
+    if (dc->dist_bytes < out_bytes) {
+      if (dc->dist) cudaFree(dc->dist);
+      dc->dist = nullptr; dc->dist_bytes = 0;
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dc->dist), out_bytes));
+      dc->dist_bytes = out_bytes;
+    }
+    d_out = dc->dist;
+  }
+  rc = run_passes(d_labels, label_bytes, ndim, sx, sy, sz, wx, wy, wz, border, flags, d_out, *dc, stream);
+  if (rc) return rc;
+  if (!out_dev) CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int edtb200_pass_first(const void* labels_dev, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
+                       float wx, int black_border, int flags, float* f_dev, int device, void* stream) {
+  int rc = check_dims(label_bytes, 3, sx, sy, sz);
+  if (rc) return rc;
+  if (sx * sy * sz == 0) return 0;
+  if (!labels_dev || !f_dev) return fail(EDTB200_EINVAL, "null pointer");
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceCache* dc = nullptr;
+  rc = probe(device, &dc);
+  if (rc) return rc;
+  const int kflags = ((flags & EDTB200_SQRT) ? edtb200::kSqrt : 0) |
+                     ((flags & EDTB200_SIGNED) ? edtb200::kZeroLabel : 0);
+  return dispatch_first(label_bytes, labels_dev, f_dev, sy * sz, sx, wx, black_border != 0, kflags, *dc,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int edtb200_pass_later(const void* labels_dev, int label_bytes, int axis, int64_t sx, int64_t sy, int64_t sz,
+                       float w, int border_lo, int border_hi, int flags, float* f_dev, int device,
+                       void* stream) {
+  int rc = check_dims(label_bytes, 3, sx, sy, sz);
+  if (rc) return rc;
+  if (axis != 1 && axis != 2) return fail(EDTB200_EINVAL, "axis must be 1 (Y) or 2 (Z)");
+  if (sx * sy * sz == 0) return 0;
+  if (!labels_dev || !f_dev) return fail(EDTB200_EINVAL, "null pointer");
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceCache* dc = nullptr;
+  rc = probe(device, &dc);
+  if (rc) return rc;
+  return dispatch_later(label_bytes, labels_dev, f_dev, geom_for_axis(axis, sx, sy, sz), w,
+                        border_lo != 0, border_hi != 0,
+                        ((flags & EDTB200_SQRT) ? edtb200::kSqrt : 0) |
+                            ((flags & EDTB200_SIGNED) ? edtb200::kNegate : 0),
+                        *dc, static_cast<cudaStream_t>(stream));
+}
+
+int edtb200_release(void) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  for (int d = 0; d < count && d < kMaxDevices; ++d) {
+    DeviceCache& dc = g_cache[d];
+    if (!dc.labels && !dc.dist && !dc.stream) continue;
+    cudaSetDevice(d);
+    if (dc.stream) { cudaStreamSynchronize(dc.stream); cudaStreamDestroy(dc.stream); }
+    if (dc.labels) cudaFree(dc.labels);
+    if (dc.dist) cudaFree(dc.dist);
+    dc = DeviceCache();
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+/* include/edt_b200.h -- C ABI of the B200-native multi-label Euclidean distance transform.
+ *
+ * This is the drop-in boundary for the reference's hot path
+ *     pyedt::_edt3dsq<T>(labels, sx,sy,sz, wx,wy,wz, black_border, parallel, workspace)
+ *                                                    (reference src/edt.hpp:411-484)
+ * and its 2-D / 1-D siblings (src/edt.hpp:632-678, 70-119), which the reference's Cython
+ * layer binds in src/edt.pyx:63-87 (`cdef extern from "edt.hpp" namespace "pyedt"`).
+ * Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * Conventions shared by every entry point
+ *   - volumes are x-fastest ("Fortran order" in the reference's words, README.md:100);
+ *     C-ordered numpy arrays are handled by the caller swapping axes (src/edt.pyx:651-664);
+ *   - labels are compared for equality only, as raw 1/2/4/8-byte unsigned integers
+ *     (the reference instantiates uint8/16/32/64, float, double and bool: src/edt.pyx:670-732;
+ *     float labels must be canonicalised by the caller so that -0.0 == +0.0);
+ *   - the output is float32, same shape; with EDTB200_OUT_ON_DEVICE the transform runs in
+ *     place in `out` (the reference's `workspace` argument has the same role);
+ *   - every function returns 0 on success or a negative EDTB200_E* code;
+ *     edtb200_last_error() gives the message (thread-local).  Nothing throws.
+ *   - there is NO CPU fallback: without a usable CUDA device every transform fails with
+ *     EDTB200_ECUDA.
+ */
+#ifndef EDT_B200_H
+#define EDT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDTB200_VERSION 100
+
+/* flags */
+#define EDTB200_SQRT             1  /* emit sqrt(edtsq): reference _edt3d (src/edt.hpp:591-604) /
+                                       np.sqrt in edt() (src/edt.pyx:241-242), fused in the last store */
+#define EDTB200_SIGNED           2  /* signed distance: background (label 0) is transformed as an
+                                       ordinary label and its result negated -- equal to the
+                                       reference's sdf()/sdfsq() = f(data) - f(data==0)
+                                       (src/edt.pyx:121-202) */
+#define EDTB200_LABELS_ON_DEVICE 4  /* `labels` is a device pointer on `device` */
+#define EDTB200_OUT_ON_DEVICE    8  /* `out` is a device pointer on `device` */
+
+/* error codes */
+#define EDTB200_EINVAL  (-1)   /* bad argument */
+#define EDTB200_ECUDA   (-2)   /* CUDA runtime / driver error, or no device */
+#define EDTB200_ENOMEM  (-3)   /* device or host allocation failed */
+#define EDTB200_ELIMIT  (-4)   /* size outside what the kernels support */
+
+int edtb200_version(void);
+const char *edtb200_last_error(void);
+
+/* Number of visible CUDA devices (0 if none or on error). */
+int edtb200_device_count(void);
+
+/* Whole transform: edtsq / edt / sdfsq / sdf of a 1-D, 2-D or 3-D volume.
+ *
+ * Replaces  pyedt::_edt3dsq<T>        src/edt.hpp:411-484   (ndim == 3)
+ *           pyedt::_edt2dsq<T>        src/edt.hpp:632-678   (ndim == 2; sz ignored)
+ *           squared_edt_1d_multi_seg  src/edt.hpp:70-119    (ndim == 1; sy, sz ignored)
+ *           pyedt::_edt3d / _edt2d    src/edt.hpp:591-604, 764-778  (EDTB200_SQRT)
+ *           edt.sdf / edt.sdfsq       src/edt.pyx:121-202   (EDTB200_SIGNED)
+ * For ndim < 3 the missing axis passes are skipped (not run on size-1 axes), exactly as the
+ * reference's lower-dimensional drivers do.
+ *
+ *   labels       sx*sy*sz labels of `label_bytes` (1, 2, 4 or 8) bytes each; never written
+ *   wx, wy, wz   anisotropy (voxel size) per axis
+ *   black_border non-zero: the volume faces count as background
+ *   out          sx*sy*sz float32
+ *   device       CUDA device ordinal
+ *   stream       cudaStream_t (as void*) or NULL.  Device-resident calls (both *_ON_DEVICE
+ *                flags) are asynchronous on `stream`; calls touching host memory return
+ *                after the result has landed in `out`.
+ */
+int edtb200_transform(const void *labels, int label_bytes, int ndim,
+                      int64_t sx, int64_t sy, int64_t sz,
+                      float wx, float wy, float wz,
+                      int black_border, int flags,
+                      float *out, int device, void *stream);
+
+/* Single axis passes on DEVICE-resident data, for callers that split a volume into Z slabs
+ * across GPUs: every rank runs the first- and second-axis passes on
+ * its slab, exchanges what the third axis needs, then runs the third-axis pass.
+ *
+ * edtb200_pass_first : replaces the X loop of _edt3dsq          src/edt.hpp:430-440
+ * edtb200_pass_later : replaces the Y or Z loop of _edt3dsq     src/edt.hpp:450-475
+ *     axis 1 = Y (stride sx), axis 2 = Z (stride sx*sy).
+ *     flags: on pass_first EDTB200_SIGNED means "background is an ordinary label" (needed for
+ *     sdf, no sign is applied there); on pass_later EDTB200_SQRT / EDTB200_SIGNED are applied
+ *     in that pass's store (sqrt, negate background) -- use them on the last pass only.
+ *     border_lo / border_hi say independently whether the low / high end of the axis is a
+ *     volume face with black_border (an interior slab face is neither).
+ */
+int edtb200_pass_first(const void *labels_dev, int label_bytes,
+                       int64_t sx, int64_t sy, int64_t sz, float wx,
+                       int black_border, int flags,
+                       float *f_dev, int device, void *stream);
+
+int edtb200_pass_later(const void *labels_dev, int label_bytes, int axis,
+                       int64_t sx, int64_t sy, int64_t sz, float w,
+                       int border_lo, int border_hi, int flags,
+                       float *f_dev, int device, void *stream);
+
+/* Free every cached device buffer / stream this library holds on all devices. */
+int edtb200_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDT_B200_H */

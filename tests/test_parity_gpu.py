@@ -1,0 +1,306 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle.
+
+Bar (BASELINE.json north_star): edtsq bit-exact on the integer squared-distance path;
+edt / sdf within 1 ULP after sqrt (0 expected: IEEE sqrt on identical inputs).  For
+non-integer anisotropy the kernels evaluate each candidate with one fused multiply-add,
+which equals the reference's double-precision evaluation rounded once except in
+astronomically rare double-rounding ties, so the same exact comparison is applied there.
+"""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz")
+
+
+def ulp_diff(a, b):
+  """Max distance in float32 ULPs (inf/nan must match exactly)."""
+  a = np.asarray(a, np.float32).ravel()
+  b = np.asarray(b, np.float32).ravel()
+  special = ~np.isfinite(a) | ~np.isfinite(b)
+  if not np.array_equal(a[special], b[special], equal_nan=True):
+    return np.inf
+  ai = a[~special].view(np.int32).astype(np.int64)
+  bi = b[~special].view(np.int32).astype(np.int64)
+  ai = np.where(ai < 0, np.int64(-2**31) - ai, ai)
+  bi = np.where(bi < 0, np.int64(-2**31) - bi, bi)
+  return 0 if ai.size == 0 else int(np.abs(ai - bi).max())
+
+
+def assert_same(got, want, what):
+  assert got.shape == want.shape, (what, got.shape, want.shape)
+  assert got.dtype == np.float32
+  if not np.array_equal(got, want, equal_nan=True):
+    bad = np.argwhere(~((got == want) | (np.isnan(got) & np.isnan(want))))
+    first = tuple(bad[0])
+    raise AssertionError("%s: %d of %d voxels differ; first at %s: got %r want %r (max ulp %s)" % (
+      what, len(bad), got.size, first, got[first], want[first], ulp_diff(got, want)))
+
+
+# ---- the reference's own golden vectors -------------------------------------------------
+
+@pytest.mark.parametrize("case", cases.KNOWN_ANSWERS, ids=[c[0] for c in cases.KNOWN_ANSWERS])
+def test_known_answers(edt, case):
+  for dtype in case[4]:
+    labels, kwargs, expected = cases.known_answer_arrays(case, dtype)
+    for parallel in (1, 2):
+      assert_same(edt.edtsq(labels, parallel=parallel, **kwargs), expected, (case[0], dtype))
+
+
+def test_one_d_simple(edt):
+  # automated_test.py:17-60
+  for dtype in cases.ALL:
+    for labels in ([0], [0, 1], [1, 0], [0, 1, 0], [0, 1, 1, 0]):
+      arr = np.array(labels, dtype=dtype)
+      for bb in (True, False):
+        assert np.all(edt.edt(arr, black_border=bb) == arr)
+    one = np.array([1], dtype=dtype)
+    assert np.all(edt.edt(one, black_border=True) == one)
+    assert np.all(edt.edt(one, black_border=False) == np.array([np.inf]))
+
+
+def test_golden_fixtures(edt):
+  z = np.load(GOLDEN)
+  for seed in z["seeds"]:
+    key = "s%d" % seed
+    labels = z[key + "_labels"]
+    an = z[key + "_aniso"]
+    an = float(an[0]) if labels.ndim == 1 else tuple(an)
+    bb = bool(z[key + "_border"])
+    assert_same(edt.edtsq(labels, anisotropy=an, black_border=bb), z[key + "_edtsq"], ("edtsq", seed))
+    assert ulp_diff(edt.edt(labels, anisotropy=an, black_border=bb), z[key + "_edt"]) <= 1, seed
+    assert ulp_diff(edt.sdf(labels, anisotropy=an, black_border=bb), z[key + "_sdf"]) <= 1, seed
+  cfg1 = np.ones((64, 64, 64), dtype=np.uint32, order="F")      # BASELINE.json configs[0]
+  got = edt.edtsq(cfg1, black_border=True, parallel=1)
+  assert_same(got, z["cfg1_edtsq"], "cfg1")
+  assert got.max() == 1024.0 and got.flags.f_contiguous
+
+
+# ---- randomized differential tests against the oracle -----------------------------------
+
+@pytest.mark.parametrize("block", range(8))
+def test_random_vs_oracle(edt, oracle, block):
+  for seed in range(block * 40, block * 40 + 40):
+    labels, kwargs = cases.random_case(seed)
+    what = (seed, labels.shape, labels.dtype.name, kwargs)
+    assert_same(edt.edtsq(labels, **kwargs), oracle.edtsq(labels, **kwargs), ("edtsq",) + what)
+    if seed % 2 == 0:
+      assert_same(edt.edt(labels, **kwargs), oracle.edt(labels, **kwargs), ("edt",) + what)
+    if seed % 3 == 0:
+      assert_same(edt.sdf(labels, **kwargs), oracle.sdf(labels, **kwargs), ("sdf",) + what)
+      assert_same(edt.sdfsq(labels, **kwargs), oracle.sdfsq(labels, **kwargs), ("sdfsq",) + what)
+
+
+@pytest.mark.parametrize("shape", [(33, 65, 97), (1, 1, 300), (300, 1, 1), (1, 300, 1), (7, 513, 3),
+                                   (70, 3, 600), (128, 128, 128), (31, 1030), (1030, 31), (5000,),
+                                   (2, 2, 2), (32, 32, 32), (64, 96, 33)])
+@pytest.mark.parametrize("kind", ["blocks", "sparse_zero", "iid", "balls"])
+def test_shapes_vs_oracle(edt, oracle, shape, kind):
+  rng = np.random.default_rng(zlib.crc32(repr((shape, kind)).encode()))
+  for dtype, order in ((np.uint32, "F"), (np.uint8, "C")):
+    labels = cases.random_volume(rng, shape, kind, dtype)
+    labels = np.asfortranarray(labels) if order == "F" else np.ascontiguousarray(labels)
+    nd = labels.ndim
+    for an in ((1.0, 1.0, 1.0), (4.0, 4.0, 40.0), (0.7, 1.3, 2.9)):
+      a = an[0] if nd == 1 else an[:nd]
+      for bb in (False, True):
+        assert_same(edt.edtsq(labels, anisotropy=a, black_border=bb),
+                    oracle.edtsq(labels, anisotropy=a, black_border=bb), (shape, kind, dtype, order, a, bb))
+
+
+def test_long_axes(edt, oracle):
+  """Lines longer than one shared-memory tile (the out-of-place long-line kernel), a first
+  axis of 46342 voxels (automated_test.py:819-823) and >4096-voxel distances."""
+  arr = np.ones((46342, 1))
+  arr[0, 0] = 0
+  got = edt.edt(arr)
+  assert not np.any(np.isnan(got))
+  assert_same(got, oracle.edt(arr), "46342x1 float64")
+  col = np.ascontiguousarray(np.ones((1, 46342), dtype=np.uint8).T)       # C order: sx=1, sy=46342
+  col[17, 0] = 0
+  assert_same(edt.edtsq(col, anisotropy=(3.0, 1.0)), oracle.edtsq(col, anisotropy=(3.0, 1.0)), "1x46342")
+  rng = np.random.default_rng(11)
+  for shape in ((3, 5, 2500), (2500, 5, 3), (4, 2100)):
+    lab = cases.random_volume(rng, shape, "blocks", np.uint16)
+    lab[lab == 0] = 7        # long runs, no background: inf-rich without a border
+    lab.flat[5] = 0
+    for bb in (False, True):
+      assert_same(edt.edtsq(lab, black_border=bb), oracle.edtsq(lab, black_border=bb), (shape, bb))
+
+
+def test_label_widths_and_float_labels(edt, oracle):
+  rng = np.random.default_rng(2)
+  base = rng.integers(0, 4, (19, 23, 29))
+  for dtype in (np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.uint64, np.int64,
+                np.float32, np.float64, bool):
+    lab = (base != 0) if dtype is bool else base.astype(dtype)
+    assert_same(edt.edtsq(lab, black_border=True), oracle.edtsq(lab, black_border=True), dtype)
+  # labels that differ only in high bits / only in sign
+  wide = np.where(base == 1, np.uint64(1) << np.uint64(63), np.uint64(base)).astype(np.uint64)
+  wide[base == 2] = (np.uint64(1) << np.uint64(63)) + np.uint64(1) << np.uint64(0)
+  assert_same(edt.edtsq(wide), oracle.edtsq(wide), "uint64 high bits")
+  neg = np.where(base == 1, -1, base).astype(np.int32)
+  assert_same(edt.edtsq(neg), oracle.edtsq(neg), "negative int32")
+  fl = base.astype(np.float32)
+  fl[base == 0] = -0.0                                   # -0.0 is background too
+  assert_same(edt.edtsq(fl), oracle.edtsq(fl), "negative zero")
+  # bool path == uint8 path (bit-identical in the reference)
+  assert_same(edt.edtsq(base != 0), edt.edtsq((base != 0).astype(np.uint8)), "bool vs uint8")
+  # unsupported dtype: the reference silently returns zeros (no else branch, src/edt.pyx:670-732)
+  assert np.all(edt.edtsq(base.astype(np.float16)) == 0)
+
+
+def test_non_contiguous_and_lists(edt, oracle):
+  rng = np.random.default_rng(4)
+  big = rng.integers(0, 3, (20, 30, 14)).astype(np.uint8)
+  view = big[::2, 1:-1, ::-1]
+  assert not view.flags.c_contiguous and not view.flags.f_contiguous
+  assert_same(edt.edtsq(view), oracle.edtsq(view), "strided view")
+  before = big.copy()
+  edt.edt(big)
+  assert np.array_equal(big, before)                       # input never mutated
+  assert_same(edt.edtsq([[1, 1, 0], [1, 2, 2]]), oracle.edtsq([[1, 1, 0], [1, 2, 2]]), "list input")
+  res = edt.edtsq(np.zeros((128, 128, 128), np.uint32), anisotropy=np.array([4, 4, 40]))   # automated_test.py:729-734
+  assert res.shape == (128, 128, 128)
+
+
+def test_reference_metamorphic_cases(edt, oracle):
+  # automated_test.py:723-727
+  assert np.all(edt.edt(np.ones((128, 128, 128), np.uint8), black_border=False, anisotropy=(1, 1, 1)) == np.inf)
+  # automated_test.py:641-649
+  box = np.zeros((15, 15, 15), dtype=bool, order="F")
+  box[2:12, 2:12, 5:10] = True
+  img = edt.edt(box, anisotropy=(1, 1, 1))
+  for i in range(1, 150, 7):
+    w = float(i)
+    assert np.all(w * img == edt.edt(box, anisotropy=(w, w, w)))
+  # automated_test.py:685-700 (C vs F order, lopsided multi-label)
+  for size in ((150, 150, 150), (150, 75, 23), (75, 150, 37)):
+    def gen(order):
+      x = np.zeros(size, dtype=np.uint32, order=order)
+      x[0:25, 5:50, 0:25] = 3
+      x[25:50, 5:50, 0:25] = 1
+      x[60:110, 5:50, 0:25] = 2
+      return x
+    c, f = edt.edt(gen("C")), edt.edt(gen("F"))
+    assert np.array_equal(c, f)
+    assert_same(c, oracle.edt(gen("C")), size)
+  # automated_test.py:800-817 anisotropy magnitudes
+  img = np.ones((100, 97, 99), dtype=np.uint8)
+  img[0, 0, 0] = 0
+  for weight in (1e-7, 1e-3, 0.1, 1.0, 1000.0, 1e8):
+    res = edt.edt(img, anisotropy=(weight,) * 3)
+    expected = np.sqrt(sum((weight * (s - 1)) ** 2 for s in img.shape))
+    assert np.isclose(res[99, 96, 98], expected, rtol=1e-6)
+    assert ulp_diff(res, oracle.edt(img, anisotropy=(weight,) * 3)) <= 1
+  # automated_test.py:702-721
+  lab = np.ones((256, 256, 256), dtype=np.uint8)
+  lab[0, 0, 0] = 0
+  lab[-1, -1, -1] = 0
+  res = edt.edt(lab, anisotropy=(1000000, 1200000, 40))
+  assert np.isfinite(res.max())
+  assert ulp_diff(res, oracle.edt(lab, anisotropy=(1000000, 1200000, 40))) <= 1
+  # automated_test.py:879-895
+  lab2 = np.zeros((9, 7), dtype=np.uint16)
+  lab2[3:6, 2:5] = 1
+  assert np.array_equal(edt.sdf(lab2), edt.edt(lab2) - edt.edt(lab2 == 0))
+
+
+# ---- device-resident path and the per-axis entry points ---------------------------------
+
+def test_torch_device_path(edt, oracle):
+  import torch
+  rng = np.random.default_rng(9)
+  lab = cases.random_volume(rng, (40, 50, 60), "blocks", np.int32)
+  t = torch.from_numpy(lab).cuda()
+  for sqrt, signed, fn in ((False, False, oracle.edtsq), (True, False, oracle.edt),
+                           (True, True, oracle.sdf), (False, True, oracle.sdfsq)):
+    got = edt.edt_cuda(t, (2.0, 3.0, 5.0), True, sqrt=sqrt, signed=signed)
+    assert got.is_cuda and got.dtype == torch.float32
+    assert_same(got.cpu().numpy(), fn(lab, anisotropy=(2.0, 3.0, 5.0), black_border=True), (sqrt, signed))
+  out = torch.empty(t.shape, dtype=torch.float32, device="cuda")
+  again = edt.edt_cuda(t, (2.0, 3.0, 5.0), True, out=out)
+  assert again.data_ptr() == out.data_ptr()
+  u8 = torch.from_numpy((lab != 0)).cuda()
+  assert_same(edt.edt_cuda(u8).cpu().numpy(), oracle.edtsq(lab != 0), "bool tensor")
+
+
+def test_per_axis_entry_points(edt, oracle):
+  """pass_first + pass_later(Y) + pass_later(Z) == transform (the slab-split building blocks)."""
+  import ctypes
+  import torch
+  rng = np.random.default_rng(10)
+  lab = np.asfortranarray(cases.random_volume(rng, (37, 41, 29), "blocks", np.uint32))
+  sx, sy, sz = lab.shape
+  t = torch.from_numpy(np.ascontiguousarray(lab.T)).cuda()        # memory = x fastest
+  f = torch.empty(t.shape, dtype=torch.float32, device="cuda")
+  lib = edt._lib()
+  s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+  assert lib.edtb200_pass_first(t.data_ptr(), 4, sx, sy, sz, 2.0, 1, 0, f.data_ptr(), 0, s) == 0
+  assert lib.edtb200_pass_later(t.data_ptr(), 4, 1, sx, sy, sz, 3.0, 1, 1, 0, f.data_ptr(), 0, s) == 0
+  assert lib.edtb200_pass_later(t.data_ptr(), 4, 2, sx, sy, sz, 5.0, 1, 1, 1, f.data_ptr(), 0, s) == 0
+  torch.cuda.synchronize()
+  got = np.asfortranarray(f.cpu().numpy().T)
+  assert_same(got, oracle.edt(lab, anisotropy=(2.0, 3.0, 5.0), black_border=True), "per-axis")
+
+
+# ---- BASELINE.json sizes: closed forms and size-independent properties ------------------
+
+def box_closed_form(shape, anisotropy):
+  """edtsq of an all-foreground box with black_border=True: the nearest background is the
+  closest face, so the value is (min over axes of w*min(i+1, n-i))^2 -- exact in float32 for
+  integer weights."""
+  axes = []
+  for n, w in zip(shape, anisotropy):
+    i = np.arange(n, dtype=np.float32)
+    axes.append((np.float32(w) * np.minimum(i + 1, n - i)) ** 2)
+  gx, gy, gz = np.meshgrid(*axes, indexing="ij", sparse=True)
+  return np.minimum(np.minimum(gx, gy), gz)
+
+
+def test_cfg3_box_512_uint8(edt):
+  # BASELINE.json configs[2]: 512^3 uint8 ones, anisotropy (6,6,30), black_border, edt vs edtsq
+  lab = np.ones((512, 512, 512), dtype=np.uint8, order="F")
+  want = np.asfortranarray(np.broadcast_to(box_closed_form(lab.shape, (6, 6, 30)), lab.shape))
+  got = edt.edtsq(lab, anisotropy=(6, 6, 30), black_border=True)
+  assert got.max() == 2359296.0
+  assert np.array_equal(got, want)
+  got = edt.edt(lab, anisotropy=(6, 6, 30), black_border=True)
+  assert np.array_equal(got, np.sqrt(want))
+
+
+def test_cfg2_512_uint32_properties(edt, oracle):
+  # BASELINE.json configs[1]: 512^3 uint32 random 0..255, anisotropy (1,1,1)
+  rng = np.random.default_rng(0)
+  lab = np.asfortranarray(rng.integers(0, 256, (512, 512, 512), dtype=np.uint32))
+  got = edt.edtsq(lab, anisotropy=(1, 1, 1))
+  assert got.flags.f_contiguous and got.shape == lab.shape
+  assert np.all(got[lab == 0] == 0) and np.all(got[lab != 0] >= 1)
+  # a slab of full x/y extent against the oracle (z-faces differ, so compare an interior band
+  # of a transform recomputed on the slab with the same neighbours: use black_border on both)
+  slab = np.asfortranarray(lab[:, :, :24])
+  assert_same(edt.edtsq(slab, black_border=True), oracle.edtsq(slab, black_border=True), "512x512x24 slab")
+  # relabelling invariance: any injective map on non-zero labels leaves the result unchanged
+  perm = rng.permutation(np.arange(1, 256, dtype=np.uint32)) * np.uint32(16777259)
+  lut = np.concatenate([[np.uint32(0)], perm]).astype(np.uint32)
+  assert np.array_equal(edt.edtsq(np.asfortranarray(lut[lab])), got)
+  # axis-order invariance: the C-ordered transpose holds the same bytes with axes reversed
+  assert np.array_equal(edt.edtsq(lab.T), got.T)
+  # exact scaling by a power of two
+  assert np.array_equal(edt.edtsq(lab, anisotropy=(4, 4, 4)), got * np.float32(16))
+
+
+def test_blocks_256_vs_oracle(edt, oracle):
+  rng = np.random.default_rng(0)
+  small = rng.integers(0, 256, (8, 8, 8), dtype=np.uint32)
+  lab = np.asfortranarray(np.repeat(np.repeat(np.repeat(small, 32, 0), 32, 1), 32, 2))   # 256^3, 32^3 blocks
+  for bb in (False, True):
+    assert_same(edt.edtsq(lab, anisotropy=(1, 1, 1), black_border=bb),
+                oracle.edtsq(lab, anisotropy=(1, 1, 1), black_border=bb), ("blocks256", bb))
+  assert_same(edt.sdf(lab, anisotropy=(4, 4, 40)), oracle.sdf(lab, anisotropy=(4, 4, 40)), "blocks256 sdf")
