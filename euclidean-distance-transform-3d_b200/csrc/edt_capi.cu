@@ -34,6 +34,29 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kMaxDevices = 64;
 
+// cuTensorMapEncodeTiled, fetched through the runtime so that libcuda is not a link-time
+// dependency (the library must load on machines without a driver, e.g. for the build check).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_encode_tried = false;
+
+EncodeTiledFn tensor_map_encoder() {
+  if (!g_encode_tried) {
+    g_encode_tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    else
+      cudaGetLastError();
+  }
+  return g_encode;
+}
+
 // Per-device cached state for calls that take host buffers.
 struct DeviceCache {
   void* labels = nullptr;
@@ -41,6 +64,11 @@ struct DeviceCache {
   float* dist = nullptr;
   size_t dist_bytes = 0;
   cudaStream_t stream = nullptr;
+  // step tables T[k] of the first-axis pass, keyed by the weight's bits (see step_table_kernel)
+  struct Table { float* data = nullptr; int count = 0; uint32_t wbits = 0; cudaEvent_t ready = nullptr;
+                 cudaStream_t built_on = nullptr; uint64_t stamp = 0; };
+  Table tables[8];
+  uint64_t table_clock = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
   bool probed = false;
@@ -80,24 +108,68 @@ int check_dims(int label_bytes, int ndim, int64_t& sx, int64_t& sy, int64_t& sz)
   return 0;
 }
 
+// Device table T[0..count) for weight w, cached per device.  Built once on `stream`; other
+// streams wait on the build event, so no host synchronisation and no per-call allocation.
+int step_table(DeviceCache& dc, float w, int count, cudaStream_t stream, const float** out) {
+  uint32_t wbits;
+  memcpy(&wbits, &w, sizeof(wbits));
+  DeviceCache::Table* hit = nullptr;
+  DeviceCache::Table* victim = &dc.tables[0];
+  for (auto& t : dc.tables) {
+    if (t.data && t.wbits == wbits && t.count >= count) { hit = &t; break; }
+    if (t.stamp < victim->stamp) victim = &t;
+  }
+  if (!hit) {
+    DeviceCache::Table& t = *victim;
+    if (t.data) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(t.data); t.data = nullptr; }
+    const int cap = count < 4096 ? 4096 : count;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&t.data), sizeof(float) * (size_t)cap));
+    if (!t.ready) CUDA_TRY(cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming));
+    edtb200::step_table_kernel<<<1, 32, 0, stream>>>(w, cap, t.data);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(t.ready, stream));
+    t.count = cap; t.wbits = wbits; t.built_on = stream;
+    hit = &t;
+  } else if (hit->built_on != stream) {
+    CUDA_TRY(cudaStreamWaitEvent(stream, hit->ready, 0));
+  }
+  hit->stamp = ++dc.table_clock;
+  *out = hit->data;
+  return 0;
+}
+
 // ---- launches ---------------------------------------------------------------------
 
 template <int Bytes>
 int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float w, int border,
-                 int flags, const DeviceCache& dc, cudaStream_t stream) {
+                 int flags, DeviceCache& dc, cudaStream_t stream) {
   using namespace edtb200;
-  const int count = (int)sx + 1;
-  float* table = nullptr;
-  CUDA_TRY(cudaMallocAsync(&table, sizeof(float) * (size_t)count, stream));
-  step_table_kernel<<<1, 32, 0, stream>>>(w, count, table);
-  CUDA_TRY(cudaGetLastError());
+  const float* table = nullptr;
+  int trc = step_table(dc, w, (int)sx + 1, stream, &table);
+  if (trc) return trc;
 
+  using LT = typename LabelOf<Bytes>::type;
+  // register-resident vector kernel when rows are short and 16-byte aligned
+  if (sx % 4 == 0 && sx <= 1024 && reinterpret_cast<uintptr_t>(labels) % (4 * Bytes) == 0 &&
+      reinterpret_cast<uintptr_t>(f) % 16 == 0) {
+    const size_t smem = sizeof(float) * (size_t)(sx + 1);
+    int64_t blocks = (nlines + 7) / 8;
+    const int64_t cap = (int64_t)dc.sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const LT* lab = static_cast<const LT*>(labels);
+    if (sx <= 128)      first_axis_vec_kernel<Bytes, 1><<<(unsigned)blocks, 256, smem, stream>>>(lab, f, nlines, (int)sx, table, border, flags);
+    else if (sx <= 256) first_axis_vec_kernel<Bytes, 2><<<(unsigned)blocks, 256, smem, stream>>>(lab, f, nlines, (int)sx, table, border, flags);
+    else if (sx <= 512) first_axis_vec_kernel<Bytes, 4><<<(unsigned)blocks, 256, smem, stream>>>(lab, f, nlines, (int)sx, table, border, flags);
+    else                first_axis_vec_kernel<Bytes, 8><<<(unsigned)blocks, 256, smem, stream>>>(lab, f, nlines, (int)sx, table, border, flags);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   const int nwords = (int)(sx >> 5) + 1;
   const size_t per_warp = sizeof(uint32_t) * 4 * (size_t)nwords;
   int warps = 8;
   while (warps > 1 && per_warp * warps > (size_t)dc.max_smem_optin) warps >>= 1;
   if (per_warp * warps > (size_t)dc.max_smem_optin) {
-    cudaFreeAsync(table, stream);
     return fail(EDTB200_ELIMIT, "first axis of %lld voxels exceeds the shared-memory line buffer",
                 (long long)sx);
   }
@@ -111,8 +183,23 @@ int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float
   kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(
       static_cast<const typename LabelOf<Bytes>::type*>(labels), f, nlines, (int)sx, table, border, flags);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaFreeAsync(table, stream));
   return 0;
+}
+
+// Tensor map over the distance volume for one later-axis pass: dims (adjacent lines, line
+// length, outer), box = 32 lines x box_rows.
+bool make_tile_map(CUtensorMap* map, float* f, const edtb200::LineGeom& g, int box_rows) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)g.inner_count, (cuuint64_t)g.n, (cuuint64_t)g.outer_count};
+  const cuuint64_t strides[2] = {(cuuint64_t)g.line_stride * sizeof(float),
+                                 (cuuint64_t)(g.outer_count > 1 ? g.outer_stride : g.line_stride * (int64_t)g.n) *
+                                     sizeof(float)};
+  const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int Bytes>
@@ -123,12 +210,42 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
   LineGeom g = g0;
   const float w2 = w * w;                       // float product, as src/edt.hpp:181
   const int nchunks = (g.n + 31) >> 5;
+  g.tiles_per_outer = (int)((g.inner_count + 31) / 32);
+  const int64_t tiles = (int64_t)g.tiles_per_outer * g.outer_count;
+  const int warps = nchunks < 16 ? nchunks : 16;
+
+  // ---- TMA-staged tile kernel: needs a 16-byte row pitch and at least one full-width tile ----
+  {
+    TileBoxes tb;
+    tb.nboxes = (g.n + 255) / 256;
+    tb.box_rows = (g.n + tb.nboxes - 1) / tb.nboxes;
+    const size_t smem = (size_t)tb.box_rows * tb.nboxes * 128 + (size_t)nchunks * 256 +
+                        (size_t)((g.n + 3) & ~1) * 4 + 16;
+    const bool aligned = reinterpret_cast<uintptr_t>(f) % 16 == 0 && g.line_stride % 4 == 0 &&
+                         (g.outer_count <= 1 || g.outer_stride % 4 == 0);
+    CUtensorMap map;
+    if (aligned && g.inner_count >= 32 && g.inner_count < (1LL << 31) && tiles <= 0x7fffffffLL &&
+        smem <= (size_t)dc.max_smem_optin && make_tile_map(&map, f, g, tb.box_rows)) {
+      if (flags) {
+        auto kern = later_axis_tma_kernel<Bytes, true>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, static_cast<const LT*>(labels), f, g, tb, w2,
+                                                            border_lo, border_hi, flags);
+      } else {
+        auto kern = later_axis_tma_kernel<Bytes, false>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, static_cast<const LT*>(labels), f, g, tb, w2,
+                                                            border_lo, border_hi, flags);
+      }
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+  }
+
+  // ---- plain tile kernel (any alignment) ----
   const size_t smem = (size_t)g.n * 128 + (size_t)nchunks * 256;
   if (smem <= (size_t)dc.max_smem_optin) {
-    g.tiles_per_outer = (int)((g.inner_count + 31) / 32);
-    const int64_t tiles = (int64_t)g.tiles_per_outer * g.outer_count;
     if (tiles > 0x7fffffffLL) return fail(EDTB200_ELIMIT, "too many line tiles");
-    int warps = nchunks < 16 ? nchunks : 16;
     auto kern = later_axis_kernel<Bytes>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(static_cast<const LT*>(labels), f, g, w2,
@@ -136,7 +253,7 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
-  // lines too long for a shared-memory tile: out of place through a temporary volume
+  // ---- lines too long for a shared-memory tile: out of place through a temporary volume ----
   const int64_t lines = g.inner_count * g.outer_count;
   const size_t bytes = sizeof(float) * (size_t)lines * (size_t)g.n;
   float* tmp = nullptr;
@@ -152,7 +269,7 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
 }
 
 int dispatch_first(int label_bytes, const void* labels, float* f, int64_t nlines, int64_t sx, float w,
-                   int border, int flags, const DeviceCache& dc, cudaStream_t s) {
+                   int border, int flags, DeviceCache& dc, cudaStream_t s) {
   switch (label_bytes) {
     case 1: return launch_first<1>(labels, f, nlines, sx, w, border, flags, dc, s);
     case 2: return launch_first<2>(labels, f, nlines, sx, w, border, flags, dc, s);
@@ -185,7 +302,7 @@ edtb200::LineGeom geom_for_axis(int axis, int64_t sx, int64_t sy, int64_t sz) {
 // All passes of one transform on device-resident buffers.
 int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_t sy, int64_t sz,
                float wx, float wy, float wz, int border, int flags, float* f,
-               const DeviceCache& dc, cudaStream_t stream) {
+               DeviceCache& dc, cudaStream_t stream) {
   using namespace edtb200;
   // sqrt / sign are applied by whichever pass is the last one; background-as-label (sdf)
   // changes the first pass only -- later passes treat every run alike.
@@ -319,8 +436,12 @@ int edtb200_release(void) {
   if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
   for (int d = 0; d < count && d < kMaxDevices; ++d) {
     DeviceCache& dc = g_cache[d];
-    if (!dc.labels && !dc.dist && !dc.stream) continue;
+    bool any = dc.labels || dc.dist || dc.stream;
+    for (auto& t : dc.tables) any = any || t.data;
+    if (!any) continue;
     cudaSetDevice(d);
+    cudaDeviceSynchronize();
+    for (auto& t : dc.tables) { if (t.data) cudaFree(t.data); if (t.ready) cudaEventDestroy(t.ready); }
     if (dc.stream) { cudaStreamSynchronize(dc.stream); cudaStreamDestroy(dc.stream); }
     if (dc.labels) cudaFree(dc.labels);
     if (dc.dist) cudaFree(dc.dist);

@@ -19,6 +19,7 @@
 // No tensor cores: there is no contraction here, the passes are HBM-bound streaming
 // kernels over the label volume and one float32 volume that is transformed in place.
 #pragma once
+#include <cuda.h>          // CUtensorMap (type only; the encoder is fetched at run time)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -180,6 +181,164 @@ first_axis_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
 }
 
 // ---------------------------------------------------------------------------------------
+// First-axis pass, register-resident variant for lines of sx <= 128*K voxels with sx % 4 == 0
+// (rows then start on 16-byte boundaries for the float4 stores and on 4*Bytes boundaries for
+// the vector label loads).  One warp per line; a lane owns 4 consecutive voxels of each
+// 128-voxel block, so every global access is a full-width vector (4*Bytes per lane in,
+// 16 bytes per lane out).  Boundaries are found in registers: per lane a 4-bit mask per
+// block, then a warp max-scan (nearest boundary at or below) and a warp min-scan (nearest
+// boundary above) with carries across the K blocks.  The step table lives in shared memory.
+// ---------------------------------------------------------------------------------------
+template <int Bytes> struct Vec4Labels;
+template <> struct Vec4Labels<1> {
+  static __device__ __forceinline__ void load(const uint8_t* p, uint32_t v[4]) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p));
+    v[0] = w & 0xffu; v[1] = (w >> 8) & 0xffu; v[2] = (w >> 16) & 0xffu; v[3] = w >> 24;
+  }
+};
+template <> struct Vec4Labels<2> {
+  static __device__ __forceinline__ void load(const uint16_t* p, uint32_t v[4]) {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = w.x & 0xffffu; v[1] = w.x >> 16; v[2] = w.y & 0xffffu; v[3] = w.y >> 16;
+  }
+};
+template <> struct Vec4Labels<4> {
+  static __device__ __forceinline__ void load(const uint32_t* p, uint32_t v[4]) {
+    const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
+    v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
+  }
+};
+template <> struct Vec4Labels<8> {
+  static __device__ __forceinline__ void load(const uint64_t* p, unsigned long long v[4]) {
+    const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+};
+
+template <int Bytes, int K>
+__global__ void __launch_bounds__(256)
+first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
+                      float* __restrict__ out, int64_t nlines, int sx,
+                      const float* __restrict__ table, int border, int flags) {
+  using LT = typename LabelOf<Bytes>::type;
+  using WT = typename LabelOf<Bytes>::wide;
+  extern __shared__ float table_s[];                 // sx + 1 entries
+  for (int i = threadIdx.x; i <= sx; i += blockDim.x) table_s[i] = __ldg(table + i);
+  __syncthreads();
+
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  const float inf = __int_as_float(0x7f800000);
+
+  for (int64_t line = (int64_t)blockIdx.x * warps + warp; line < nlines;
+       line += (int64_t)gridDim.x * warps) {
+    const LT* __restrict__ src = labels + line * sx;
+    float* __restrict__ dst = out + line * sx;
+
+    // ---- labels -> per-block 4-bit "label changes here" and "is background" masks ----
+    WT v[K][4];
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+      const int q0 = (b << 7) + (lane << 2);
+      if (q0 < sx) Vec4Labels<Bytes>::load(src + q0, v[b]);
+      else { v[b][0] = v[b][1] = v[b][2] = v[b][3] = 0; }
+    }
+    uint32_t edges = 0, zeros = 0;                   // 4 bits per block
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+      const int q0 = (b << 7) + (lane << 2);
+      WT up = __shfl_up_sync(full, v[b][3], 1);
+      if (b > 0) {                                    // compile-time: warp-uniform
+        const WT tail = __shfl_sync(full, v[b > 0 ? b - 1 : 0][3], 31);
+        if (lane == 0) up = tail;
+      }
+      uint32_t m = 0, z = 0;
+      if (q0 < sx) {
+        const bool first = (q0 == 0);
+        if (first ? (border != 0) : (v[b][0] != up)) m |= 1u;
+        if (v[b][1] != v[b][0]) m |= 2u;
+        if (v[b][2] != v[b][1]) m |= 4u;
+        if (v[b][3] != v[b][2]) m |= 8u;
+        if (v[b][0] == 0) z |= 1u;
+        if (v[b][1] == 0) z |= 2u;
+        if (v[b][2] == 0) z |= 4u;
+        if (v[b][3] == 0) z |= 8u;
+      }
+      edges |= m << (4 * b);
+      zeros |= z << (4 * b);
+    }
+
+    // ---- nearest boundary at or below the lane's first voxel, per block (max-scan) ----
+    int lb_in[K], nb_in[K];
+    int carry = -1;
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+      const int q0 = (b << 7) + (lane << 2);
+      const uint32_t m = (edges >> (4 * b)) & 15u;
+      int hi = m ? (q0 + 31 - __clz(m)) : -1;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const int o = __shfl_up_sync(full, hi, s);
+        if (lane >= s) hi = max(hi, o);
+      }
+      int excl = __shfl_up_sync(full, hi, 1);
+      if (lane == 0) excl = -1;
+      lb_in[b] = max(excl, carry);
+      carry = max(carry, __shfl_sync(full, hi, 31));
+    }
+    // ---- nearest boundary above the lane's last voxel, per block (min-scan, reversed) ----
+    carry = border ? sx : kNoBoundary;
+#pragma unroll
+    for (int b = K - 1; b >= 0; --b) {
+      const int q0 = (b << 7) + (lane << 2);
+      const uint32_t m = (edges >> (4 * b)) & 15u;
+      int lo = m ? (q0 + __ffs(m) - 1) : kNoBoundary;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const int o = __shfl_down_sync(full, lo, s);
+        if (lane + s < 32) lo = min(lo, o);
+      }
+      int excl = __shfl_down_sync(full, lo, 1);
+      if (lane == 31) excl = kNoBoundary;
+      nb_in[b] = min(excl, carry);
+      carry = min(carry, __shfl_sync(full, lo, 0));
+    }
+
+    // ---- distances, table lookup, vector store ----
+#pragma unroll
+    for (int b = 0; b < K; ++b) {
+      const int q0 = (b << 7) + (lane << 2);
+      if (q0 >= sx) continue;
+      const uint32_t m = (edges >> (4 * b)) & 15u;
+      const uint32_t z = (zeros >> (4 * b)) & 15u;
+      int lbe[4], nbe[4];
+      int lb = lb_in[b];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { if ((m >> e) & 1u) lb = q0 + e; lbe[e] = lb; }
+      int nb = nb_in[b];
+#pragma unroll
+      for (int e = 3; e >= 0; --e) { nbe[e] = nb; if ((m >> e) & 1u) nb = q0 + e; }
+      float r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int q = q0 + e;
+        const int kl = (lbe[e] >= 0) ? (q - lbe[e] + 1) : kNoBoundary;
+        const int kr = (nbe[e] != kNoBoundary) ? (nbe[e] - q) : kNoBoundary;
+        const int k = min(kl, kr);
+        const bool background = (z >> e) & 1u;
+        float val = (k >= kNoBoundary) ? inf : table_s[k];
+        if (background && !(flags & kZeroLabel)) val = 0.0f;
+        r[e] = finish_value(val, background, flags);
+      }
+      *reinterpret_cast<float4*>(dst + q0) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Later-axis pass (Y: line stride sx, Z: line stride sx*sy), in place on f.
 //
 // A CTA owns a tile of 32 adjacent lines (32 consecutive x, i.e. 128 B per row, every
@@ -298,6 +457,197 @@ later_axis_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
       }
       const bool background = (wzero >> r) & 1u;
       f[base + (int64_t)i * ls] = finish_value(best, background, flags);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Later-axis pass, TMA variant (used whenever the volume's row pitch is a multiple of 16
+// bytes).  Same tile (whole lines x 32 adjacent lines) and same arithmetic as
+// later_axis_kernel, but
+//   * the float32 tile is fetched by the TMA unit (cp.async.bulk.tensor, 3-D tensor map over
+//     the distance volume, boxes of 32 x <=256 rows) while the threads turn the label
+//     column into run-start bit words, so the LSU only carries the label stream;
+//     out-of-range columns of ragged tiles are zero-filled by the hardware;
+//   * voxels that form a run of length one (the common case in dense segmentations and the
+//     only case in iid-random labels) take a two-instruction path: min(f, w2);
+//   * border terms w2*e^2 come from a small shared-memory table instead of int->float
+//     conversions.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a tile load that never completes (bad tensor map) traps instead of hanging.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  for (unsigned spin = 0; spin < (1u << 26); ++spin)
+    if (mbar_try_wait(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(smem_addr(bar))
+      : "memory");
+}
+
+struct TileBoxes {
+  int box_rows;   // rows per TMA box (<= 256)
+  int nboxes;     // boxes per tile; box_rows * nboxes >= n
+};
+
+template <int Bytes, bool Epilogue>
+__global__ void __launch_bounds__(512)
+later_axis_tma_kernel(const __grid_constant__ CUtensorMap fmap,
+                      const typename LabelOf<Bytes>::type* __restrict__ labels,
+                      float* __restrict__ f, LineGeom g, TileBoxes tb, float w2,
+                      int border_lo, int border_hi, int flags) {
+  using LT = typename LabelOf<Bytes>::type;
+  extern __shared__ __align__(128) unsigned char smem_tile[];
+
+  const int n = g.n;
+  const int nchunks = (n + 31) >> 5;
+  const int rows_alloc = tb.box_rows * tb.nboxes;
+  float* fs = reinterpret_cast<float*>(smem_tile);                           // [rows_alloc][32]
+  uint32_t* startw = reinterpret_cast<uint32_t*>(fs + (size_t)rows_alloc * 32);   // [nchunks][32]
+  uint32_t* zerow = startw + (size_t)nchunks * 32;                           // [nchunks][32]
+  float* sq = reinterpret_cast<float*>(zerow + (size_t)nchunks * 32);        // [n + 2]: w2*e^2
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sq + ((n + 2 + 1) & ~1));
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+
+  const int64_t tile = blockIdx.x;
+  const int64_t outer = tile / g.tiles_per_outer;
+  const int64_t inner0 = (tile - outer * g.tiles_per_outer) * 32;
+  const bool live = (inner0 + lane) < g.inner_count;
+  const int64_t base = outer * g.outer_stride + inner0 + lane;
+  const int64_t ls = g.line_stride;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_expect_tx(bar, (unsigned)rows_alloc * 128u);
+    for (int b = 0; b < tb.nboxes; ++b)
+      tma_load_3d(fs + (size_t)b * tb.box_rows * 32, &fmap, (int)inner0, b * tb.box_rows, (int)outer, bar);
+  }
+
+  // ---- labels -> run-start / background words; border-term table ----
+  for (int i = threadIdx.x; i < n + 2; i += blockDim.x) {
+    const float e = (float)i;
+    sq[i] = __fmul_rn(w2, __fmul_rn(e, e));
+  }
+  for (int c = warp; c < nchunks; c += warps) {
+    const int i0 = c << 5;
+    uint32_t wstart = 0, wzero = 0;
+    if (live) {
+      const LT* __restrict__ col = labels + base + (int64_t)i0 * ls;
+      LT prev = (i0 > 0) ? col[-ls] : (LT)0;
+      if (i0 + 32 <= n) {
+#pragma unroll 16
+        for (int r = 0; r < 32; ++r) {
+          const LT here = col[(int64_t)r * ls];
+          if (here != prev) wstart |= (1u << r);
+          if (here == 0) wzero |= (1u << r);
+          prev = here;
+        }
+      } else {
+        for (int r = 0; r < n - i0; ++r) {
+          const LT here = col[(int64_t)r * ls];
+          if (here != prev) wstart |= (1u << r);
+          if (here == 0) wzero |= (1u << r);
+          prev = here;
+        }
+        wstart |= 1u << (n - i0);          // pretend a run starts at row n (line end)
+      }
+      if (i0 == 0) wstart |= 1u;           // a run starts at row 0 by definition
+    }
+    startw[(size_t)c * 32 + lane] = wstart;
+    zerow[(size_t)c * 32 + lane] = wzero;
+  }
+  __syncthreads();         // words + table visible; also orders the mbarrier init before the waits
+  mbar_wait(bar, 0);       // float tile has landed
+  if (!live) return;
+
+  const float inf = __int_as_float(0x7f800000);
+
+  for (int c = warp; c < nchunks; c += warps) {
+    const int i0 = c << 5;
+    const int rows = min(32, n - i0);
+    const uint32_t wstart = startw[(size_t)c * 32 + lane];
+    const uint32_t wzero = zerow[(size_t)c * 32 + lane];
+    // bit r of `nextw`: a run starts at row i0 + r + 1 (the line end counts as a start)
+    uint32_t ext = 1u;
+    if (i0 + 32 < n) ext = startw[(size_t)(c + 1) * 32 + lane] & 1u;
+    const uint32_t nextw = (wstart >> 1) | (ext << 31);
+    uint32_t single = wstart & nextw;                    // runs of length one
+    if (!border_lo && c == 0) single &= ~1u;             // rows without a border term go the long way
+    if (!border_hi && i0 + 32 >= n) single &= ~(1u << (n - 1 - i0));
+
+    // run start at or before this chunk's first row, first run start after this chunk
+    int prev_lo = 0;
+    for (int cc = c - 1; cc >= 0; --cc) {
+      const uint32_t w = startw[(size_t)cc * 32 + lane];
+      if (w) { prev_lo = (cc << 5) + 31 - __clz(w); break; }
+    }
+    int next_hi = n;
+    if (!ext) {
+      for (int cc = c + 1; cc < nchunks; ++cc) {
+        uint32_t w = startw[(size_t)cc * 32 + lane];
+        if (w) { next_hi = min(n, (cc << 5) + __ffs(w) - 1); break; }
+      }
+    } else {
+      next_hi = min(n, i0 + 32);
+    }
+
+    const float* frow = fs + (size_t)i0 * 32 + lane;
+    float* __restrict__ dst = f + base + (int64_t)i0 * ls;
+    for (int r = 0; r < rows; ++r) {
+      const int i = i0 + r;
+      float best = frow[r * 32];
+      if ((single >> r) & 1u) {
+        best = fminf(best, w2);
+      } else {
+        const uint32_t mlo = wstart & (0xffffffffu >> (31 - r));
+        const int run_lo = mlo ? (i0 + 31 - __clz(mlo)) : prev_lo;
+        const uint32_t mhi = nextw & (0xffffffffu << r);
+        const int run_hi = mhi ? (i0 + __ffs(mhi)) : next_hi;          // exclusive
+        const int dl = i - run_lo;
+        const int dr = run_hi - 1 - i;
+        const float lo_term = (run_lo > 0 || border_lo) ? sq[dl + 1] : inf;
+        const float hi_term = (run_hi < n || border_hi) ? sq[dr + 1] : inf;
+        best = fminf(best, fminf(lo_term, hi_term));
+        const int dmax = max(dl, dr);
+        float fd = 1.0f;
+        for (int d = 1; d <= dmax; ++d, fd += 1.0f) {
+          const float t = __fmul_rn(fd, fd);
+          if (!(__fmul_rn(w2, t) < best)) break;
+          if (d <= dl) best = fminf(best, __fmaf_rn(w2, t, frow[(r - d) * 32]));
+          if (d <= dr) best = fminf(best, __fmaf_rn(w2, t, frow[(r + d) * 32]));
+        }
+      }
+      if (Epilogue) best = finish_value(best, (wzero >> r) & 1u, flags);
+      dst[(int64_t)r * ls] = best;
     }
   }
 }
