@@ -152,16 +152,26 @@ int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float
   // register-resident vector kernel when rows are short and 16-byte aligned
   if (sx % 4 == 0 && sx <= 1024 && reinterpret_cast<uintptr_t>(labels) % (4 * Bytes) == 0 &&
       reinterpret_cast<uintptr_t>(f) % 16 == 0) {
-    const size_t smem = sizeof(float) * (size_t)(sx + 1);
+    const size_t smem = sizeof(float) * (size_t)(sx + 2);
     int64_t blocks = (nlines + 7) / 8;
     const int64_t cap = (int64_t)dc.sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const LT* lab = static_cast<const LT*>(labels);
-    if (sx <= 128)      first_axis_vec_kernel<Bytes, 1><<<(unsigned)blocks, 256, smem, stream>>>(lab, f, nlines, (int)sx, table, border, flags);
-    else if (sx <= 256) first_axis_vec_kernel<Bytes, 2><<<(unsigned)blocks, 256, smem, stream>>>(lab, f, nlines, (int)sx, table, border, flags);
-    else if (sx <= 512) first_axis_vec_kernel<Bytes, 4><<<(unsigned)blocks, 256, smem, stream>>>(lab, f, nlines, (int)sx, table, border, flags);
-    else                first_axis_vec_kernel<Bytes, 8><<<(unsigned)blocks, 256, smem, stream>>>(lab, f, nlines, (int)sx, table, border, flags);
+#define EDT_LAUNCH_VEC(KK)                                                                         \
+  do {                                                                                           \
+    if (flags == 0)                                                                              \
+      first_axis_vec_kernel<Bytes, KK, true><<<(unsigned)blocks, 256, smem, stream>>>(            \
+          lab, f, nlines, (int)sx, table, border, flags);                                        \
+    else                                                                                         \
+      first_axis_vec_kernel<Bytes, KK, false><<<(unsigned)blocks, 256, smem, stream>>>(           \
+          lab, f, nlines, (int)sx, table, border, flags);                                        \
+  } while (0)
+    if (sx <= 128)      EDT_LAUNCH_VEC(1);
+    else if (sx <= 256) EDT_LAUNCH_VEC(2);
+    else if (sx <= 512) EDT_LAUNCH_VEC(4);
+    else                EDT_LAUNCH_VEC(8);
+#undef EDT_LAUNCH_VEC
     CUDA_TRY(cudaGetLastError());
     return 0;
   }
@@ -224,7 +234,8 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
     const bool aligned = reinterpret_cast<uintptr_t>(f) % 16 == 0 && g.line_stride % 4 == 0 &&
                          (g.outer_count <= 1 || g.outer_stride % 4 == 0);
     CUtensorMap map;
-    if (aligned && g.inner_count >= 32 && g.inner_count < (1LL << 31) && tiles <= 0x7fffffffLL &&
+    const bool fits32 = (int64_t)g.n * g.line_stride + 64 < (1LL << 32);
+    if (aligned && fits32 && g.inner_count >= 32 && g.inner_count < (1LL << 31) && tiles <= 0x7fffffffLL &&
         smem <= (size_t)dc.max_smem_optin && make_tile_map(&map, f, g, tb.box_rows)) {
       if (flags) {
         auto kern = later_axis_tma_kernel<Bytes, true>;

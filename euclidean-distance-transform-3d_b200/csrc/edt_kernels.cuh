@@ -216,29 +216,34 @@ template <> struct Vec4Labels<8> {
   }
 };
 
-template <int Bytes, int K>
+// Plain = true: squared EDT, background forced to 0, no sqrt / sign (the hot configuration);
+// Plain = false: behaviour selected by `flags` at run time.
+template <int Bytes, int K, bool Plain>
 __global__ void __launch_bounds__(256)
 first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
                       float* __restrict__ out, int64_t nlines, int sx,
                       const float* __restrict__ table, int border, int flags) {
   using LT = typename LabelOf<Bytes>::type;
   using WT = typename LabelOf<Bytes>::wide;
-  extern __shared__ float table_s[];                 // sx + 1 entries
+  extern __shared__ float table_s[];                 // T[0..sx], then +inf at sx + 1
   for (int i = threadIdx.x; i <= sx; i += blockDim.x) table_s[i] = __ldg(table + i);
+  if (threadIdx.x == 0) table_s[sx + 1] = __int_as_float(0x7f800000);
   __syncthreads();
 
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps = blockDim.x >> 5;
-  const float inf = __int_as_float(0x7f800000);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned gt_mask = (lane == 31) ? 0u : (0xfffffffeu << lane);
+  const bool keep_background = Plain ? false : (flags & kZeroLabel) != 0;
 
   for (int64_t line = (int64_t)blockIdx.x * warps + warp; line < nlines;
        line += (int64_t)gridDim.x * warps) {
     const LT* __restrict__ src = labels + line * sx;
     float* __restrict__ dst = out + line * sx;
 
-    // ---- labels -> per-block 4-bit "label changes here" and "is background" masks ----
+    // ---- labels -> per-block 4-bit "label changes here" / "is background" masks ----
     WT v[K][4];
 #pragma unroll
     for (int b = 0; b < K; ++b) {
@@ -247,18 +252,18 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
       else { v[b][0] = v[b][1] = v[b][2] = v[b][3] = 0; }
     }
     uint32_t edges = 0, zeros = 0;                   // 4 bits per block
+    uint32_t occ[K];                                 // lanes owning at least one boundary
 #pragma unroll
     for (int b = 0; b < K; ++b) {
       const int q0 = (b << 7) + (lane << 2);
       WT up = __shfl_up_sync(full, v[b][3], 1);
-      if (b > 0) {                                    // compile-time: warp-uniform
+      if (b > 0) {                                   // compile-time: warp-uniform
         const WT tail = __shfl_sync(full, v[b > 0 ? b - 1 : 0][3], 31);
         if (lane == 0) up = tail;
       }
       uint32_t m = 0, z = 0;
       if (q0 < sx) {
-        const bool first = (q0 == 0);
-        if (first ? (border != 0) : (v[b][0] != up)) m |= 1u;
+        if ((q0 == 0) ? (border != 0) : (v[b][0] != up)) m |= 1u;
         if (v[b][1] != v[b][0]) m |= 2u;
         if (v[b][2] != v[b][1]) m |= 4u;
         if (v[b][3] != v[b][2]) m |= 8u;
@@ -267,71 +272,70 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
         if (v[b][2] == 0) z |= 4u;
         if (v[b][3] == 0) z |= 8u;
       }
+      occ[b] = __ballot_sync(full, m != 0);
       edges |= m << (4 * b);
       zeros |= z << (4 * b);
     }
 
-    // ---- nearest boundary at or below the lane's first voxel, per block (max-scan) ----
-    int lb_in[K], nb_in[K];
-    int carry = -1;
+    // ---- nearest boundary strictly below / above the lane's 4 voxels, per block ----
+    // The ballots give the boundary-owning lanes; one shuffle fetches that lane's masks.
+    int kl_in[K], kr_in[K];          // kL of the voxel just below q0, kR seed for q0 + 3
+    {
+      uint32_t prev_occ = 0; int prev_b = 0;
 #pragma unroll
-    for (int b = 0; b < K; ++b) {
-      const int q0 = (b << 7) + (lane << 2);
-      const uint32_t m = (edges >> (4 * b)) & 15u;
-      int hi = m ? (q0 + 31 - __clz(m)) : -1;
-#pragma unroll
-      for (int s = 1; s < 32; s <<= 1) {
-        const int o = __shfl_up_sync(full, hi, s);
-        if (lane >= s) hi = max(hi, o);
+      for (int b = 0; b < K; ++b) {
+        const int q0 = (b << 7) + (lane << 2);
+        const uint32_t mine = occ[b] & lt_mask;
+        const uint32_t pick = mine ? mine : prev_occ;
+        const int pb = mine ? b : prev_b;
+        const int sl = 31 - __clz(pick | 1u);
+        const uint32_t nib = (__shfl_sync(full, edges, sl) >> (4 * pb)) & 15u;
+        const int pos = (pb << 7) + (sl << 2) + 31 - __clz(nib | 1u);
+        kl_in[b] = pick ? (q0 - pos) : kNoBoundary;          // = kL(q0 - 1) + ... see below
+        if (occ[b]) { prev_occ = occ[b]; prev_b = b; }
       }
-      int excl = __shfl_up_sync(full, hi, 1);
-      if (lane == 0) excl = -1;
-      lb_in[b] = max(excl, carry);
-      carry = max(carry, __shfl_sync(full, hi, 31));
-    }
-    // ---- nearest boundary above the lane's last voxel, per block (min-scan, reversed) ----
-    carry = border ? sx : kNoBoundary;
+      uint32_t next_occ = 0; int next_b = 0;
 #pragma unroll
-    for (int b = K - 1; b >= 0; --b) {
-      const int q0 = (b << 7) + (lane << 2);
-      const uint32_t m = (edges >> (4 * b)) & 15u;
-      int lo = m ? (q0 + __ffs(m) - 1) : kNoBoundary;
-#pragma unroll
-      for (int s = 1; s < 32; s <<= 1) {
-        const int o = __shfl_down_sync(full, lo, s);
-        if (lane + s < 32) lo = min(lo, o);
+      for (int b = K - 1; b >= 0; --b) {
+        const int q0 = (b << 7) + (lane << 2);
+        const uint32_t mine = occ[b] & gt_mask;
+        const uint32_t pick = mine ? mine : next_occ;
+        const int pb = mine ? b : next_b;
+        const int sl = __ffs(pick | 0x80000000u) - 1;
+        const uint32_t nib = (__shfl_sync(full, edges, sl) >> (4 * pb)) & 15u;
+        const int pos = (pb << 7) + (sl << 2) + __ffs(nib | 8u) - 1;
+        const int far = border ? (sx - (q0 + 3)) : kNoBoundary;
+        kr_in[b] = pick ? (pos - (q0 + 3)) : far;
+        if (occ[b]) { next_occ = occ[b]; next_b = b; }
       }
-      int excl = __shfl_down_sync(full, lo, 1);
-      if (lane == 31) excl = kNoBoundary;
-      nb_in[b] = min(excl, carry);
-      carry = min(carry, __shfl_sync(full, lo, 0));
     }
 
-    // ---- distances, table lookup, vector store ----
+    // ---- distances (chains over the 4 voxels), table lookup, vector store ----
 #pragma unroll
     for (int b = 0; b < K; ++b) {
       const int q0 = (b << 7) + (lane << 2);
       if (q0 >= sx) continue;
       const uint32_t m = (edges >> (4 * b)) & 15u;
       const uint32_t z = (zeros >> (4 * b)) & 15u;
-      int lbe[4], nbe[4];
-      int lb = lb_in[b];
+      // kL(q) = q - (nearest boundary position <= q) + 1:  1 at a boundary, else previous + 1
+      int kl[4], kr[4];
+      int run = kl_in[b];                    // q0 - pos: kL the voxel q0 would have without its own bit
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { if ((m >> e) & 1u) lb = q0 + e; lbe[e] = lb; }
-      int nb = nb_in[b];
+      for (int e = 0; e < 4; ++e) { run = ((m >> e) & 1u) ? 1 : run + 1; kl[e] = run; }
+      // kR(q) = (nearest boundary position > q) - q:  1 if q + 1 is a boundary, else next + 1
+      run = kr_in[b];
+      kr[3] = run;
 #pragma unroll
-      for (int e = 3; e >= 0; --e) { nbe[e] = nb; if ((m >> e) & 1u) nb = q0 + e; }
+      for (int e = 2; e >= 0; --e) { run = ((m >> (e + 1)) & 1u) ? 1 : run + 1; kr[e] = run; }
       float r[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int q = q0 + e;
-        const int kl = (lbe[e] >= 0) ? (q - lbe[e] + 1) : kNoBoundary;
-        const int kr = (nbe[e] != kNoBoundary) ? (nbe[e] - q) : kNoBoundary;
-        const int k = min(kl, kr);
+        int k = min(min(kl[e], kr[e]), sx + 1);          // sx + 1 -> +inf (no boundary at all)
         const bool background = (z >> e) & 1u;
-        float val = (k >= kNoBoundary) ? inf : table_s[k];
-        if (background && !(flags & kZeroLabel)) val = 0.0f;
-        r[e] = finish_value(val, background, flags);
+        if (background && !keep_background) k = 0;        // T[0] = 0
+        float val = table_s[k];
+        if (!Plain) val = finish_value(val, background, flags);
+        r[e] = val;
       }
       *reinterpret_cast<float4*>(dst + q0) = make_float4(r[0], r[1], r[2], r[3]);
     }
@@ -542,8 +546,10 @@ later_axis_tma_kernel(const __grid_constant__ CUtensorMap fmap,
   const int64_t outer = tile / g.tiles_per_outer;
   const int64_t inner0 = (tile - outer * g.tiles_per_outer) * 32;
   const bool live = (inner0 + lane) < g.inner_count;
-  const int64_t base = outer * g.outer_stride + inner0 + lane;
-  const int64_t ls = g.line_stride;
+  // CTA-uniform tile origin + 32-bit element offsets (the host guarantees n * line_stride < 2^32)
+  const LT* __restrict__ tl = labels + (outer * g.outer_stride + inner0);
+  float* __restrict__ tf = f + (outer * g.outer_stride + inner0);
+  const uint32_t ls = (uint32_t)g.line_stride;
 
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
@@ -561,21 +567,23 @@ later_axis_tma_kernel(const __grid_constant__ CUtensorMap fmap,
     const int i0 = c << 5;
     uint32_t wstart = 0, wzero = 0;
     if (live) {
-      const LT* __restrict__ col = labels + base + (int64_t)i0 * ls;
-      LT prev = (i0 > 0) ? col[-ls] : (LT)0;
+      uint32_t idx = (uint32_t)i0 * ls + (uint32_t)lane;
+      LT prev = (i0 > 0) ? tl[idx - ls] : (LT)0;
       if (i0 + 32 <= n) {
-#pragma unroll 16
+#pragma unroll
         for (int r = 0; r < 32; ++r) {
-          const LT here = col[(int64_t)r * ls];
+          const LT here = tl[idx];
+          idx += ls;
           if (here != prev) wstart |= (1u << r);
-          if (here == 0) wzero |= (1u << r);
+          if (Epilogue && here == 0) wzero |= (1u << r);
           prev = here;
         }
       } else {
         for (int r = 0; r < n - i0; ++r) {
-          const LT here = col[(int64_t)r * ls];
+          const LT here = tl[idx];
+          idx += ls;
           if (here != prev) wstart |= (1u << r);
-          if (here == 0) wzero |= (1u << r);
+          if (Epilogue && here == 0) wzero |= (1u << r);
           prev = here;
         }
         wstart |= 1u << (n - i0);          // pretend a run starts at row n (line end)
@@ -583,7 +591,7 @@ later_axis_tma_kernel(const __grid_constant__ CUtensorMap fmap,
       if (i0 == 0) wstart |= 1u;           // a run starts at row 0 by definition
     }
     startw[(size_t)c * 32 + lane] = wstart;
-    zerow[(size_t)c * 32 + lane] = wzero;
+    if (Epilogue) zerow[(size_t)c * 32 + lane] = wzero;
   }
   __syncthreads();         // words + table visible; also orders the mbarrier init before the waits
   mbar_wait(bar, 0);       // float tile has landed
@@ -595,7 +603,7 @@ later_axis_tma_kernel(const __grid_constant__ CUtensorMap fmap,
     const int i0 = c << 5;
     const int rows = min(32, n - i0);
     const uint32_t wstart = startw[(size_t)c * 32 + lane];
-    const uint32_t wzero = zerow[(size_t)c * 32 + lane];
+    const uint32_t wzero = Epilogue ? zerow[(size_t)c * 32 + lane] : 0u;
     // bit r of `nextw`: a run starts at row i0 + r + 1 (the line end counts as a start)
     uint32_t ext = 1u;
     if (i0 + 32 < n) ext = startw[(size_t)(c + 1) * 32 + lane] & 1u;
@@ -610,44 +618,64 @@ later_axis_tma_kernel(const __grid_constant__ CUtensorMap fmap,
       const uint32_t w = startw[(size_t)cc * 32 + lane];
       if (w) { prev_lo = (cc << 5) + 31 - __clz(w); break; }
     }
-    int next_hi = n;
+    int next_hi = min(n, i0 + 32);
     if (!ext) {
+      next_hi = n;
       for (int cc = c + 1; cc < nchunks; ++cc) {
-        uint32_t w = startw[(size_t)cc * 32 + lane];
+        const uint32_t w = startw[(size_t)cc * 32 + lane];
         if (w) { next_hi = min(n, (cc << 5) + __ffs(w) - 1); break; }
       }
-    } else {
-      next_hi = min(n, i0 + 32);
     }
 
-    const float* frow = fs + (size_t)i0 * 32 + lane;
-    float* __restrict__ dst = f + base + (int64_t)i0 * ls;
-    for (int r = 0; r < rows; ++r) {
+    const float* fp0 = fs + (size_t)i0 * 32 + lane;
+    const uint32_t oidx0 = (uint32_t)i0 * ls + (uint32_t)lane;
+
+    // (1) runs of length one: min(f, w2); value computed unconditionally, store predicated
+    char* const op0 = reinterpret_cast<char*>(tf + oidx0);
+    const size_t pitch = (size_t)ls * sizeof(float);
+    if (rows == 32) {
+      char* op = op0;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        float v = fminf(fp0[r * 32], w2);
+        if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
+        if (single & (1u << r)) *reinterpret_cast<float*>(op) = v;
+        op += pitch;
+      }
+    } else {
+      for (int r = 0; r < rows; ++r) {
+        float v = fminf(fp0[r * 32], w2);
+        if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
+        if (single & (1u << r)) *reinterpret_cast<float*>(op0 + (size_t)r * pitch) = v;
+      }
+    }
+
+    // (2) everything else: outward scan over the voxel's own run
+    uint32_t slow = ~single & (rows == 32 ? 0xffffffffu : ((1u << rows) - 1u));
+    while (slow) {
+      const int r = __ffs(slow) - 1;
+      slow &= slow - 1u;
       const int i = i0 + r;
-      float best = frow[r * 32];
-      if ((single >> r) & 1u) {
-        best = fminf(best, w2);
-      } else {
-        const uint32_t mlo = wstart & (0xffffffffu >> (31 - r));
-        const int run_lo = mlo ? (i0 + 31 - __clz(mlo)) : prev_lo;
-        const uint32_t mhi = nextw & (0xffffffffu << r);
-        const int run_hi = mhi ? (i0 + __ffs(mhi)) : next_hi;          // exclusive
-        const int dl = i - run_lo;
-        const int dr = run_hi - 1 - i;
-        const float lo_term = (run_lo > 0 || border_lo) ? sq[dl + 1] : inf;
-        const float hi_term = (run_hi < n || border_hi) ? sq[dr + 1] : inf;
-        best = fminf(best, fminf(lo_term, hi_term));
-        const int dmax = max(dl, dr);
-        float fd = 1.0f;
-        for (int d = 1; d <= dmax; ++d, fd += 1.0f) {
-          const float t = __fmul_rn(fd, fd);
-          if (!(__fmul_rn(w2, t) < best)) break;
-          if (d <= dl) best = fminf(best, __fmaf_rn(w2, t, frow[(r - d) * 32]));
-          if (d <= dr) best = fminf(best, __fmaf_rn(w2, t, frow[(r + d) * 32]));
-        }
+      const float* fp = fp0 + r * 32;
+      const uint32_t mlo = wstart & (0xffffffffu >> (31 - r));
+      const int run_lo = mlo ? (i0 + 31 - __clz(mlo)) : prev_lo;
+      const uint32_t mhi = nextw & (0xffffffffu << r);
+      const int run_hi = mhi ? (i0 + __ffs(mhi)) : next_hi;          // exclusive
+      const int dl = i - run_lo;
+      const int dr = run_hi - 1 - i;
+      const float lo_term = (run_lo > 0 || border_lo) ? sq[dl + 1] : inf;
+      const float hi_term = (run_hi < n || border_hi) ? sq[dr + 1] : inf;
+      float best = fminf(*fp, fminf(lo_term, hi_term));
+      const int dmax = max(dl, dr);
+      float fd = 1.0f;
+      for (int d = 1; d <= dmax; ++d, fd += 1.0f) {
+        const float t = __fmul_rn(fd, fd);
+        if (!(__fmul_rn(w2, t) < best)) break;
+        if (d <= dl) best = fminf(best, __fmaf_rn(w2, t, fp[-d * 32]));
+        if (d <= dr) best = fminf(best, __fmaf_rn(w2, t, fp[d * 32]));
       }
       if (Epilogue) best = finish_value(best, (wzero >> r) & 1u, flags);
-      dst[(int64_t)r * ls] = best;
+      *reinterpret_cast<float*>(op0 + (size_t)r * pitch) = best;
     }
   }
 }
