@@ -9,6 +9,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -197,19 +198,60 @@ int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float
 }
 
 // Tensor map over the distance volume for one later-axis pass: dims (adjacent lines, line
-// length, outer), box = 32 lines x box_rows.
-bool make_tile_map(CUtensorMap* map, float* f, const edtb200::LineGeom& g, int box_rows) {
+// length, outer), box = tx lines x box_rows.
+bool make_tile_map(CUtensorMap* map, float* f, const edtb200::LineGeom& g, int tx, int box_rows) {
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)g.inner_count, (cuuint64_t)g.n, (cuuint64_t)g.outer_count};
   const cuuint64_t strides[2] = {(cuuint64_t)g.line_stride * sizeof(float),
                                  (cuuint64_t)(g.outer_count > 1 ? g.outer_stride : g.line_stride * (int64_t)g.n) *
                                      sizeof(float)};
-  const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t box[3] = {(cuuint32_t)tx, (cuuint32_t)box_rows, 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Shared memory of one tile of `tx` lines (see later_axis_tile_kernel).
+size_t tile_smem_bytes(int n, int tx, int rows_alloc) {
+  const int nchunks = (n + 31) >> 5;
+  return (size_t)rows_alloc * tx * 4 + (size_t)nchunks * tx * 16 + (size_t)((n + 3) & ~1) * 4 + 16;
+}
+
+template <int Bytes, int TX>
+int launch_tile(const void* labels, float* f, edtb200::LineGeom g, float w2, int border_lo, int border_hi,
+                int flags, bool use_tma, cudaStream_t stream) {
+  using namespace edtb200;
+  using LT = typename LabelOf<Bytes>::type;
+  const int nchunks = (g.n + 31) >> 5;
+  TileBoxes tb;
+  tb.nboxes = (g.n + 255) / 256;
+  tb.box_rows = (g.n + tb.nboxes - 1) / tb.nboxes;
+  if (tb.nboxes > 1) tb.box_rows = (tb.box_rows + 3) & ~3;      // keeps every box 128-byte aligned
+  g.tiles_per_outer = (int)((g.inner_count + TX - 1) / TX);
+  const int64_t tiles = (int64_t)g.tiles_per_outer * g.outer_count;
+  if (tiles > 0x7fffffffLL) return fail(EDTB200_ELIMIT, "too many line tiles");
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (use_tma && !make_tile_map(&map, f, g, TX, tb.box_rows)) use_tma = false;
+  const int rows_alloc = use_tma ? tb.box_rows * tb.nboxes : g.n;
+  const size_t smem = tile_smem_bytes(g.n, TX, rows_alloc);
+  constexpr int SUBS = 32 / TX;
+  int warps = (nchunks + SUBS - 1) / SUBS;
+  if (warps > 16) warps = 16;
+  const LT* lab = static_cast<const LT*>(labels);
+#define EDT_LAUNCH_TILE(EPI, TMA)                                                                   \
+  do {                                                                                              \
+    auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA>;                                        \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, lab, f, g, tb, w2, border_lo, border_hi, flags); \
+  } while (0)
+  if (flags) { if (use_tma) EDT_LAUNCH_TILE(true, true); else EDT_LAUNCH_TILE(true, false); }
+  else       { if (use_tma) EDT_LAUNCH_TILE(false, true); else EDT_LAUNCH_TILE(false, false); }
+#undef EDT_LAUNCH_TILE
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 template <int Bytes>
@@ -219,50 +261,37 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
   using LT = typename LabelOf<Bytes>::type;
   LineGeom g = g0;
   const float w2 = w * w;                       // float product, as src/edt.hpp:181
-  const int nchunks = (g.n + 31) >> 5;
-  g.tiles_per_outer = (int)((g.inner_count + 31) / 32);
-  const int64_t tiles = (int64_t)g.tiles_per_outer * g.outer_count;
-  const int warps = nchunks < 16 ? nchunks : 16;
 
-  // ---- TMA-staged tile kernel: needs a 16-byte row pitch and at least one full-width tile ----
-  {
-    TileBoxes tb;
-    tb.nboxes = (g.n + 255) / 256;
-    tb.box_rows = (g.n + tb.nboxes - 1) / tb.nboxes;
-    const size_t smem = (size_t)tb.box_rows * tb.nboxes * 128 + (size_t)nchunks * 256 +
-                        (size_t)((g.n + 3) & ~1) * 4 + 16;
+  // ---- shared-memory tile kernel: whole lines x TX adjacent lines per CTA ----
+  const bool fits32 = (int64_t)g.n * g.line_stride + 64 < (1LL << 32);
+  if (fits32 && g.n <= 4096 && g.inner_count < (1LL << 31)) {
     const bool aligned = reinterpret_cast<uintptr_t>(f) % 16 == 0 && g.line_stride % 4 == 0 &&
                          (g.outer_count <= 1 || g.outer_stride % 4 == 0);
-    CUtensorMap map;
-    const bool fits32 = (int64_t)g.n * g.line_stride + 64 < (1LL << 32);
-    if (aligned && fits32 && g.inner_count >= 32 && g.inner_count < (1LL << 31) && tiles <= 0x7fffffffLL &&
-        smem <= (size_t)dc.max_smem_optin && make_tile_map(&map, f, g, tb.box_rows)) {
-      if (flags) {
-        auto kern = later_axis_tma_kernel<Bytes, true>;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, static_cast<const LT*>(labels), f, g, tb, w2,
-                                                            border_lo, border_hi, flags);
-      } else {
-        auto kern = later_axis_tma_kernel<Bytes, false>;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, static_cast<const LT*>(labels), f, g, tb, w2,
-                                                            border_lo, border_hi, flags);
-      }
-      CUDA_TRY(cudaGetLastError());
-      return 0;
+    // Tile width: 128-byte rows (TX = 32) keep DRAM pages and L2 lines whole and measured
+    // fastest whenever at least 2 CTAs fit per SM; narrower tiles only for long lines.
+    static const size_t budgets[3] = {75 * 1024, 113 * 1024, 0};   // 3, 2, 1 CTAs per SM
+    int tx = 0;
+    for (int cand = 32; cand >= 8 && !tx; cand >>= 1) {
+      const int nb = (g.n + 255) / 256;
+      int br = (g.n + nb - 1) / nb;
+      if (nb > 1) br = (br + 3) & ~3;
+      if (tile_smem_bytes(g.n, cand, br * nb) <= budgets[1]) tx = cand;
     }
-  }
-
-  // ---- plain tile kernel (any alignment) ----
-  const size_t smem = (size_t)g.n * 128 + (size_t)nchunks * 256;
-  if (smem <= (size_t)dc.max_smem_optin) {
-    if (tiles > 0x7fffffffLL) return fail(EDTB200_ELIMIT, "too many line tiles");
-    auto kern = later_axis_kernel<Bytes>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(static_cast<const LT*>(labels), f, g, w2,
-                                                        border_lo, border_hi, flags);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    if (!tx) {
+      const int nb = (g.n + 255) / 256;
+      int br = (g.n + nb - 1) / nb;
+      if (nb > 1) br = (br + 3) & ~3;
+      if (tile_smem_bytes(g.n, 8, br * nb) <= (size_t)dc.max_smem_optin) tx = 8;
+    }
+    (void)budgets;
+    if (tx) {
+      const bool use_tma = aligned && g.inner_count >= tx;
+      switch (tx) {
+        case 32: return launch_tile<Bytes, 32>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream);
+        case 16: return launch_tile<Bytes, 16>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream);
+        default: return launch_tile<Bytes, 8>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream);
+      }
+    }
   }
   // ---- lines too long for a shared-memory tile: out of place through a temporary volume ----
   const int64_t lines = g.inner_count * g.outer_count;
@@ -310,6 +339,16 @@ edtb200::LineGeom geom_for_axis(int axis, int64_t sx, int64_t sy, int64_t sz) {
   return g;
 }
 
+// Bytes of (labels + distances) per X/Y slab; 0 disables slabbing.  EDTB200_XY_SLAB_MB overrides.
+int64_t xy_slab_bytes() {
+  static int64_t cached = -1;
+  if (cached < 0) {
+    const char* env = getenv("EDTB200_XY_SLAB_MB");
+    cached = (env ? atoll(env) : 0) * (int64_t)(1 << 20);
+  }
+  return cached;
+}
+
 // All passes of one transform on device-resident buffers.
 int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_t sy, int64_t sz,
                float wx, float wy, float wz, int border, int flags, float* f,
@@ -319,12 +358,33 @@ int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_
   // changes the first pass only -- later passes treat every run alike.
   const int epilogue = ((flags & EDTB200_SQRT) ? kSqrt : 0) | ((flags & EDTB200_SIGNED) ? kNegate : 0);
   const int zero_label = (flags & EDTB200_SIGNED) ? kZeroLabel : 0;
-  int rc = dispatch_first(label_bytes, labels, f, sy * sz, sx, wx, border,
-                          zero_label | (ndim == 1 ? epilogue : 0), dc, stream);
-  if (rc) return rc;
-  if (ndim >= 2) {
-    rc = dispatch_later(label_bytes, labels, f, geom_for_axis(1, sx, sy, sz), wy, border, border,
-                        ndim == 2 ? epilogue : 0, dc, stream);
+  int rc = 0;
+  if (ndim < 3) {
+    rc = dispatch_first(label_bytes, labels, f, sy * sz, sx, wx, border,
+                        zero_label | (ndim == 1 ? epilogue : 0), dc, stream);
+    if (rc) return rc;
+    if (ndim == 2) {
+      rc = dispatch_later(label_bytes, labels, f, geom_for_axis(1, sx, sy, sz), wy, border, border,
+                          epilogue, dc, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  // 3-D: the X and Y passes only couple voxels of one z-slice, so they are run slab by slab
+  // (X then Y on the same few slices) with slabs sized to stay resident in the 126 MB L2:
+  // the Y pass then finds the labels and the X pass's distances in L2 and HBM sees the label
+  // slab once and the distance slab once (written after Y) instead of 5 voxel-sized streams.
+  const int64_t slice_bytes = sx * sy * (int64_t)(label_bytes + 4);
+  int64_t slab = xy_slab_bytes() / (slice_bytes > 0 ? slice_bytes : 1);
+  if (slab < 1) slab = 1;
+  if (xy_slab_bytes() <= 0 || slab > sz) slab = sz;
+  for (int64_t z0 = 0; z0 < sz; z0 += slab) {
+    const int64_t zc = (sz - z0 < slab) ? (sz - z0) : slab;
+    const char* lab0 = static_cast<const char*>(labels) + z0 * sx * sy * label_bytes;
+    float* f0 = f + z0 * sx * sy;
+    rc = dispatch_first(label_bytes, lab0, f0, sy * zc, sx, wx, border, zero_label, dc, stream);
+    if (rc) return rc;
+    rc = dispatch_later(label_bytes, lab0, f0, geom_for_axis(1, sx, sy, zc), wy, border, border, 0, dc, stream);
     if (rc) return rc;
   }
   if (ndim >= 3) {

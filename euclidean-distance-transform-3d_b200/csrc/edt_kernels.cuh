@@ -345,15 +345,26 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
 // ---------------------------------------------------------------------------------------
 // Later-axis pass (Y: line stride sx, Z: line stride sx*sy), in place on f.
 //
-// A CTA owns a tile of 32 adjacent lines (32 consecutive x, i.e. 128 B per row, every
-// global access a full coalesced line) times the whole line length n, staged in shared
-// memory:  fs[n][32] float32  +  one 32-bit "run starts here" word per (32 rows, line).
-// Thread (lane = line, warp = 32-row chunk) builds the word of its chunk from the labels,
-// then produces the 32 outputs of its chunk.  For each output the search is a two-sided
-// scan outwards over its own run that stops as soon as w2*d^2 alone reaches the best value
-// found so far; candidates are evaluated with one fused multiply-add each, which is the
-// correctly rounded value of w2*d^2 + f[v] -- what the reference computes in double and
-// rounds once (src/edt.hpp:225-230).  Run borders enter as the two closed-form terms.
+// A CTA owns a tile of TX adjacent lines (TX = 32, 16 or 8 consecutive x: 128/64/32 B per
+// row, so every global access is made of whole 32-byte sectors) times the whole line length
+// n, staged in shared memory:
+//     fs[n][TX] float32   the distance tile, fetched by the TMA unit (cp.async.bulk.tensor over
+//                         a 3-D tensor map of the volume; ragged tiles are zero-filled by the
+//                         hardware) while the threads work on the labels;
+//     startw[n/32][TX]    one 32-bit "a run of equal labels starts here" word per 32 rows;
+//     hull_own/in[n/32][TX]  lower-envelope membership bits (the scan's vertex stack, 1 bit/voxel);
+//     sq[n+2]             w2*e^2, the closed-form border terms.
+// Thread (x = lane % TX, chunk = 32 consecutive rows) turns its label column into a run-start
+// word, then produces the outputs of the runs that START in its chunk:
+//   * runs of length one (the common case in dense segmentations, the only case for iid
+//     labels): out = min(f, w2) -- a predicated straight-line loop over the 32 rows;
+//   * every other run: Felzenszwalb-Huttenlocher lower envelope over the run, restated for
+//     one thread per run: vertices with f = +inf are not sites; a vertex is dropped when
+//     its intersection with the newcomer lies at or left of its intersection with the
+//     vertex below it (compared by cross-multiplication in double, no division); the
+//     read-out walks the hull and evaluates each candidate with one fused multiply-add,
+//     which is the correctly rounded w2*d^2 + f[v] the reference computes in double and
+//     rounds once (src/edt.hpp:225-230); run borders enter as sq[] terms.
 // ---------------------------------------------------------------------------------------
 struct LineGeom {
   int64_t outer_count;     // Y pass: sz            Z pass: 1
@@ -361,123 +372,14 @@ struct LineGeom {
   int64_t inner_count;     // Y pass: sx            Z pass: sx*sy   (adjacent lines)
   int64_t line_stride;     // Y pass: sx            Z pass: sx*sy
   int n;                   // line length
-  int tiles_per_outer;     // ceil(inner_count / 32)
+  int tiles_per_outer;     // ceil(inner_count / TX)
 };
 
-template <int Bytes>
-__global__ void __launch_bounds__(512)
-later_axis_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
-                  float* __restrict__ f, LineGeom g, float w2,
-                  int border_lo, int border_hi, int flags) {
-  using LT = typename LabelOf<Bytes>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+struct TileBoxes {
+  int box_rows;   // rows per TMA box (<= 256)
+  int nboxes;     // boxes per tile; box_rows * nboxes >= n
+};
 
-  const int n = g.n;
-  const int nchunks = (n + 31) >> 5;
-  float* fs = reinterpret_cast<float*>(smem_raw);                      // [n][32]
-  uint32_t* startw = reinterpret_cast<uint32_t*>(fs + (size_t)n * 32); // [nchunks][32]
-  uint32_t* zerow = startw + (size_t)nchunks * 32;                     // [nchunks][32]
-
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int warps = blockDim.x >> 5;
-
-  const int64_t tile = blockIdx.x;
-  const int64_t outer = tile / g.tiles_per_outer;
-  const int64_t inner0 = (tile - outer * g.tiles_per_outer) * 32;
-  const bool live = (inner0 + lane) < g.inner_count;
-  const int64_t base = outer * g.outer_stride + inner0 + lane;
-  const int64_t ls = g.line_stride;
-
-  // ---- stage: f tile and run-start words ----
-  for (int c = warp; c < nchunks; c += warps) {
-    const int i0 = c << 5;
-    uint32_t wstart = 0, wzero = 0;
-    if (live) {
-      LT prev = (i0 > 0) ? labels[base + (int64_t)(i0 - 1) * ls] : (LT)0;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int i = i0 + r;
-        if (i < n) {
-          const int64_t at = base + (int64_t)i * ls;
-          const LT here = labels[at];
-          fs[(size_t)i * 32 + lane] = f[at];
-          if (i > 0 && here != prev) wstart |= (1u << r);
-          if (here == 0) wzero |= (1u << r);
-          prev = here;
-        }
-      }
-    }
-    startw[(size_t)c * 32 + lane] = wstart;
-    zerow[(size_t)c * 32 + lane] = wzero;
-  }
-  __syncthreads();
-  if (!live) return;
-
-  // ---- compute ----
-  for (int c = warp; c < nchunks; c += warps) {
-    const int i0 = c << 5;
-    const uint32_t wstart = startw[(size_t)c * 32 + lane];
-    const uint32_t wzero = zerow[(size_t)c * 32 + lane];
-
-    // start of the run that is open when this chunk begins (0 = line start)
-    int run_lo = 0;
-    for (int cc = c - 1; cc >= 0; --cc) {
-      const uint32_t w = startw[(size_t)cc * 32 + lane];
-      if (w) { run_lo = (cc << 5) + 31 - __clz(w); break; }
-    }
-    // first run start after this chunk (n = line end)
-    int next_hi = n;
-    for (int cc = c + 1; cc < nchunks; ++cc) {
-      const uint32_t w = startw[(size_t)cc * 32 + lane];
-      if (w) { next_hi = (cc << 5) + __ffs(w) - 1; break; }
-    }
-
-    for (int r = 0; r < 32; ++r) {
-      const int i = i0 + r;
-      if (i >= n) break;
-      if ((wstart >> r) & 1u) run_lo = i;
-      const uint32_t later = (r == 31) ? 0u : (wstart & (0xfffffffeu << r));
-      const int run_hi = later ? (i0 + __ffs(later) - 1) : next_hi;   // exclusive
-
-      const int dl = i - run_lo;          // in-run candidates below i
-      const int dr = run_hi - 1 - i;      // in-run candidates above i
-      float best = fs[(size_t)i * 32 + lane];
-      if (run_lo > 0 || border_lo) {
-        const float e = (float)(dl + 1);
-        best = fminf(best, __fmul_rn(w2, __fmul_rn(e, e)));
-      }
-      if (run_hi < n || border_hi) {
-        const float e = (float)(dr + 1);
-        best = fminf(best, __fmul_rn(w2, __fmul_rn(e, e)));
-      }
-      const int dmax = max(dl, dr);
-      float fd = 1.0f;
-      for (int d = 1; d <= dmax; ++d, fd += 1.0f) {
-        const float t = __fmul_rn(fd, fd);
-        if (!(__fmul_rn(w2, t) < best)) break;
-        if (d <= dl) best = fminf(best, __fmaf_rn(w2, t, fs[(size_t)(i - d) * 32 + lane]));
-        if (d <= dr) best = fminf(best, __fmaf_rn(w2, t, fs[(size_t)(i + d) * 32 + lane]));
-      }
-      const bool background = (wzero >> r) & 1u;
-      f[base + (int64_t)i * ls] = finish_value(best, background, flags);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// Later-axis pass, TMA variant (used whenever the volume's row pitch is a multiple of 16
-// bytes).  Same tile (whole lines x 32 adjacent lines) and same arithmetic as
-// later_axis_kernel, but
-//   * the float32 tile is fetched by the TMA unit (cp.async.bulk.tensor, 3-D tensor map over
-//     the distance volume, boxes of 32 x <=256 rows) while the threads turn the label
-//     column into run-start bit words, so the LSU only carries the label stream;
-//     out-of-range columns of ragged tiles are zero-filled by the hardware;
-//   * voxels that form a run of length one (the common case in dense segmentations and the
-//     only case in iid-random labels) take a two-instruction path: min(f, w2);
-//   * border terms w2*e^2 come from a small shared-memory table instead of int->float
-//     conversions.
-// ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -515,64 +417,179 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-struct TileBoxes {
-  int box_rows;   // rows per TMA box (<= 256)
-  int nboxes;     // boxes per tile; box_rows * nboxes >= n
+// Hull membership bits of one line: bit (pos & 31) of word (pos >> 5) says "pos is a vertex of
+// the lower envelope".  Two arrays keep writers apart without atomics: a run's bits go to
+// `own` for the rows of the chunk it starts in and to `in` for the rows of later chunks (at
+// most one run can enter a chunk from below, and the runs starting in a chunk are all
+// processed, one after the other, by that chunk's thread).
+template <int TX>
+struct HullBits {
+  uint32_t* own;   // &hull_own[0][x], row stride TX
+  uint32_t* in;    // &hull_in[0][x]
+  int ca;          // chunk in which the current run starts
+  __device__ __forceinline__ uint32_t load(int wi) const { return (wi == ca ? own : in)[wi * TX]; }
+  __device__ __forceinline__ void store(int wi, uint32_t v) const { (wi == ca ? own : in)[wi * TX] = v; }
 };
 
-template <int Bytes, bool Epilogue>
+// Smallest hull vertex position in (after, b), or -1.
+template <int TX>
+__device__ __forceinline__ int hull_next_vertex(const HullBits<TX> hb, int after, int b) {
+  const int pos = after + 1;
+  if (pos >= b) return -1;
+  const int wlast = (b - 1) >> 5;
+  int wi = pos >> 5;
+  uint32_t m = hb.load(wi) & (0xffffffffu << (pos & 31));
+  while (m == 0u) {
+    if (wi == wlast) return -1;
+    ++wi;
+    m = hb.load(wi);
+  }
+  const int v = (wi << 5) + __ffs(m) - 1;
+  return v < b ? v : -1;
+}
+
+// Lower envelope of the parabolas rooted at the finite samples of one run [a, b) of one line.
+//   fcol : &fs[0][x] (row stride TX floats)
+//   out  : byte address of the line's row 0 in global memory, `pitch` bytes between rows
+template <int TX, bool Epilogue>
+__device__ __forceinline__ void envelope_run(const float* __restrict__ fcol, HullBits<TX> hb, int a, int b,
+                                             float w2f, bool lo_border, bool hi_border,
+                                             const float* __restrict__ sq, char* __restrict__ out,
+                                             size_t pitch, bool background, int flags) {
+  const float inf = __int_as_float(0x7f800000);
+  const double w2 = (double)w2f;
+  const int wa = a >> 5;
+  const uint32_t amask = 0xffffffffu << (a & 31);
+
+  // ---- build: drop every vertex hidden by its neighbours ----
+  int cw = wa;                   // word currently held in `cur`
+  uint32_t cur = hb.load(wa);    // bits of earlier runs (positions < a) are left alone
+  int cnt = 0;                   // vertices on the hull
+  int q = 0, p = 0;              // top vertex and the one below it
+  double fq = 0.0;               // f[q]
+  double num = 0.0, den = 1.0;   // s(p,q) = num / (2*w2*den), kept as the pair (num, den)
+  for (int r = a; r < b; ++r) {
+    if ((r >> 5) != cw) { hb.store(cw, cur); cw = r >> 5; cur = 0u; }
+    const float frf = fcol[r * TX];
+    if (!(frf < inf)) continue;                       // +inf: not a site
+    const double fr = (double)frf;
+    double num_r = 0.0, den_r = 1.0;
+    while (cnt >= 1) {
+      den_r = (double)(r - q);
+      num_r = (fr - fq) + w2 * (den_r * (double)(r + q));
+      if (cnt == 1) break;                            // the bottom vertex is never dropped
+      if (num_r * den > num * den_r) break;           // s(q,r) > s(p,q): q stays
+      {                                               // drop q
+        const int wq = q >> 5;
+        const uint32_t bit = 1u << (q & 31);
+        if (wq == cw) cur &= ~bit; else hb.store(wq, hb.load(wq) & ~bit);
+      }
+      --cnt;
+      q = p;
+      fq = (double)fcol[q * TX];
+      if (cnt >= 2) {                                 // vertex below the new top
+        int wi = q >> 5;
+        uint32_t m = (wi == cw ? cur : hb.load(wi)) & ((1u << (q & 31)) - 1u);
+        if (wi == wa) m &= amask;
+        while (m == 0u) { --wi; m = hb.load(wi); if (wi == wa) m &= amask; }
+        p = (wi << 5) + 31 - __clz(m);
+        den = (double)(q - p);
+        num = (fq - (double)fcol[p * TX]) + w2 * (den * (double)(q + p));
+      }
+    }
+    cur |= 1u << (r & 31);
+    ++cnt;
+    p = q; num = num_r; den = den_r;
+    q = r; fq = fr;
+  }
+  hb.store(cw, cur);
+
+  // ---- read out: walk the hull, one fused multiply-add per candidate ----
+  int v = hull_next_vertex<TX>(hb, a - 1, b);
+  int v1 = (v >= 0) ? hull_next_vertex<TX>(hb, v, b) : -1;
+  float fv = inf, fv1 = inf, dv = 0.0f, dv1 = 0.0f;   // dv = (float)(i - v)
+  if (v >= 0) { fv = fcol[v * TX]; dv = (float)(a - v); }
+  if (v1 >= 0) { fv1 = fcol[v1 * TX]; dv1 = (float)(a - v1); }
+  char* dst = out + (size_t)a * pitch;
+  for (int i = a; i < b; ++i) {
+    float best = inf;
+    if (v >= 0) {
+      best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
+      while (v1 >= 0) {
+        const float cand = __fmaf_rn(w2f, __fmul_rn(dv1, dv1), fv1);
+        if (!(cand <= best)) break;
+        best = cand; v = v1; fv = fv1; dv = dv1;
+        v1 = hull_next_vertex<TX>(hb, v1, b);
+        if (v1 >= 0) { fv1 = fcol[v1 * TX]; dv1 = (float)(i - v1); }
+      }
+      dv += 1.0f; dv1 += 1.0f;
+    }
+    if (lo_border) best = fminf(best, sq[i - a + 1]);
+    if (hi_border) best = fminf(best, sq[b - i]);
+    if (Epilogue) best = finish_value(best, background, flags);   // a run has one label
+    *reinterpret_cast<float*>(dst) = best;
+    dst += pitch;
+  }
+}
+
+template <int Bytes, int TX, bool Epilogue, bool UseTMA>
 __global__ void __launch_bounds__(512)
-later_axis_tma_kernel(const __grid_constant__ CUtensorMap fmap,
-                      const typename LabelOf<Bytes>::type* __restrict__ labels,
-                      float* __restrict__ f, LineGeom g, TileBoxes tb, float w2,
-                      int border_lo, int border_hi, int flags) {
+later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
+                       const typename LabelOf<Bytes>::type* __restrict__ labels,
+                       float* __restrict__ f, LineGeom g, TileBoxes tb, float w2,
+                       int border_lo, int border_hi, int flags) {
   using LT = typename LabelOf<Bytes>::type;
   extern __shared__ __align__(128) unsigned char smem_tile[];
+  constexpr int SUBS = 32 / TX;                       // chunks handled side by side by one warp
 
   const int n = g.n;
   const int nchunks = (n + 31) >> 5;
-  const int rows_alloc = tb.box_rows * tb.nboxes;
-  float* fs = reinterpret_cast<float*>(smem_tile);                           // [rows_alloc][32]
-  uint32_t* startw = reinterpret_cast<uint32_t*>(fs + (size_t)rows_alloc * 32);   // [nchunks][32]
-  uint32_t* zerow = startw + (size_t)nchunks * 32;                           // [nchunks][32]
-  float* sq = reinterpret_cast<float*>(zerow + (size_t)nchunks * 32);        // [n + 2]: w2*e^2
+  const int rows_alloc = UseTMA ? tb.box_rows * tb.nboxes : n;
+  float* fs = reinterpret_cast<float*>(smem_tile);                               // [rows_alloc][TX]
+  uint32_t* startw = reinterpret_cast<uint32_t*>(fs + (size_t)rows_alloc * TX);  // [nchunks][TX]
+  uint32_t* zerow = startw + (size_t)nchunks * TX;                               // [nchunks][TX]
+  uint32_t* hull_own = zerow + (size_t)nchunks * TX;                             // [nchunks][TX]
+  uint32_t* hull_in = hull_own + (size_t)nchunks * TX;                           // [nchunks][TX]
+  float* sq = reinterpret_cast<float*>(hull_in + (size_t)nchunks * TX);          // [n + 2]
   uint64_t* bar = reinterpret_cast<uint64_t*>(sq + ((n + 2 + 1) & ~1));
 
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int warps = blockDim.x >> 5;
+  const int x = lane & (TX - 1);
+  const int chunk0 = (threadIdx.x >> 5) * SUBS + (lane / TX);
+  const int chunk_step = (blockDim.x >> 5) * SUBS;
 
   const int64_t tile = blockIdx.x;
   const int64_t outer = tile / g.tiles_per_outer;
-  const int64_t inner0 = (tile - outer * g.tiles_per_outer) * 32;
-  const bool live = (inner0 + lane) < g.inner_count;
+  const int64_t inner0 = (tile - outer * g.tiles_per_outer) * TX;
+  const bool live = (inner0 + x) < g.inner_count;
   // CTA-uniform tile origin + 32-bit element offsets (the host guarantees n * line_stride < 2^32)
   const LT* __restrict__ tl = labels + (outer * g.outer_stride + inner0);
   float* __restrict__ tf = f + (outer * g.outer_stride + inner0);
   const uint32_t ls = (uint32_t)g.line_stride;
 
-  if (threadIdx.x == 0) {
+  if (UseTMA && threadIdx.x == 0) {
     mbar_init(bar, 1);
-    mbar_expect_tx(bar, (unsigned)rows_alloc * 128u);
-    for (int b = 0; b < tb.nboxes; ++b)
-      tma_load_3d(fs + (size_t)b * tb.box_rows * 32, &fmap, (int)inner0, b * tb.box_rows, (int)outer, bar);
+    mbar_expect_tx(bar, (unsigned)rows_alloc * (unsigned)(TX * sizeof(float)));
+    for (int bx = 0; bx < tb.nboxes; ++bx)
+      tma_load_3d(fs + (size_t)bx * tb.box_rows * TX, &fmap, (int)inner0, bx * tb.box_rows, (int)outer, bar);
   }
 
-  // ---- labels -> run-start / background words; border-term table ----
+  // ---- labels -> run-start / background words; border-term table; (plain loads of f) ----
   for (int i = threadIdx.x; i < n + 2; i += blockDim.x) {
     const float e = (float)i;
     sq[i] = __fmul_rn(w2, __fmul_rn(e, e));
   }
-  for (int c = warp; c < nchunks; c += warps) {
+  for (int c = chunk0; c < nchunks; c += chunk_step) {
     const int i0 = c << 5;
     uint32_t wstart = 0, wzero = 0;
     if (live) {
-      uint32_t idx = (uint32_t)i0 * ls + (uint32_t)lane;
+      uint32_t idx = (uint32_t)i0 * ls + (uint32_t)x;
       LT prev = (i0 > 0) ? tl[idx - ls] : (LT)0;
       if (i0 + 32 <= n) {
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
           const LT here = tl[idx];
+          if (!UseTMA) fs[(size_t)(i0 + r) * TX + x] = tf[idx];
           idx += ls;
           if (here != prev) wstart |= (1u << r);
           if (Epilogue && here == 0) wzero |= (1u << r);
@@ -581,6 +598,7 @@ later_axis_tma_kernel(const __grid_constant__ CUtensorMap fmap,
       } else {
         for (int r = 0; r < n - i0; ++r) {
           const LT here = tl[idx];
+          if (!UseTMA) fs[(size_t)(i0 + r) * TX + x] = tf[idx];
           idx += ls;
           if (here != prev) wstart |= (1u << r);
           if (Epilogue && here == 0) wzero |= (1u << r);
@@ -590,92 +608,74 @@ later_axis_tma_kernel(const __grid_constant__ CUtensorMap fmap,
       }
       if (i0 == 0) wstart |= 1u;           // a run starts at row 0 by definition
     }
-    startw[(size_t)c * 32 + lane] = wstart;
-    if (Epilogue) zerow[(size_t)c * 32 + lane] = wzero;
+    startw[(size_t)c * TX + x] = wstart;
+    if (Epilogue) zerow[(size_t)c * TX + x] = wzero;
+    hull_own[(size_t)c * TX + x] = 0u;
+    hull_in[(size_t)c * TX + x] = 0u;
   }
-  __syncthreads();         // words + table visible; also orders the mbarrier init before the waits
-  mbar_wait(bar, 0);       // float tile has landed
+  __syncthreads();         // words, table (and plain-loaded tile) visible; orders the mbarrier init
+  if (UseTMA) mbar_wait(bar, 0);       // float tile has landed
   if (!live) return;
 
-  const float inf = __int_as_float(0x7f800000);
-
-  for (int c = warp; c < nchunks; c += warps) {
+  for (int c = chunk0; c < nchunks; c += chunk_step) {
     const int i0 = c << 5;
     const int rows = min(32, n - i0);
-    const uint32_t wstart = startw[(size_t)c * 32 + lane];
-    const uint32_t wzero = Epilogue ? zerow[(size_t)c * 32 + lane] : 0u;
+    const uint32_t wstart = startw[(size_t)c * TX + x];
+    const uint32_t wzero = Epilogue ? zerow[(size_t)c * TX + x] : 0u;
     // bit r of `nextw`: a run starts at row i0 + r + 1 (the line end counts as a start)
     uint32_t ext = 1u;
-    if (i0 + 32 < n) ext = startw[(size_t)(c + 1) * 32 + lane] & 1u;
+    if (i0 + 32 < n) ext = startw[(size_t)(c + 1) * TX + x] & 1u;
     const uint32_t nextw = (wstart >> 1) | (ext << 31);
     uint32_t single = wstart & nextw;                    // runs of length one
-    if (!border_lo && c == 0) single &= ~1u;             // rows without a border term go the long way
+    if (!border_lo && c == 0) single &= ~1u;             // rows lacking a border term go the long way
     if (!border_hi && i0 + 32 >= n) single &= ~(1u << (n - 1 - i0));
 
-    // run start at or before this chunk's first row, first run start after this chunk
-    int prev_lo = 0;
-    for (int cc = c - 1; cc >= 0; --cc) {
-      const uint32_t w = startw[(size_t)cc * 32 + lane];
-      if (w) { prev_lo = (cc << 5) + 31 - __clz(w); break; }
-    }
-    int next_hi = min(n, i0 + 32);
-    if (!ext) {
-      next_hi = n;
-      for (int cc = c + 1; cc < nchunks; ++cc) {
-        const uint32_t w = startw[(size_t)cc * 32 + lane];
-        if (w) { next_hi = min(n, (cc << 5) + __ffs(w) - 1); break; }
-      }
-    }
-
-    const float* fp0 = fs + (size_t)i0 * 32 + lane;
-    const uint32_t oidx0 = (uint32_t)i0 * ls + (uint32_t)lane;
+    const float* fp0 = fs + (size_t)i0 * TX + x;
+    char* const op0 = reinterpret_cast<char*>(tf + ((uint32_t)i0 * ls + (uint32_t)x));
+    const size_t pitch = (size_t)ls * sizeof(float);
 
     // (1) runs of length one: min(f, w2); value computed unconditionally, store predicated
-    char* const op0 = reinterpret_cast<char*>(tf + oidx0);
-    const size_t pitch = (size_t)ls * sizeof(float);
     if (rows == 32) {
       char* op = op0;
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
-        float v = fminf(fp0[r * 32], w2);
+        float v = fminf(fp0[r * TX], w2);
         if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
         if (single & (1u << r)) *reinterpret_cast<float*>(op) = v;
         op += pitch;
       }
     } else {
       for (int r = 0; r < rows; ++r) {
-        float v = fminf(fp0[r * 32], w2);
+        float v = fminf(fp0[r * TX], w2);
         if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
         if (single & (1u << r)) *reinterpret_cast<float*>(op0 + (size_t)r * pitch) = v;
       }
     }
 
-    // (2) everything else: outward scan over the voxel's own run
-    uint32_t slow = ~single & (rows == 32 ? 0xffffffffu : ((1u << rows) - 1u));
-    while (slow) {
-      const int r = __ffs(slow) - 1;
-      slow &= slow - 1u;
-      const int i = i0 + r;
-      const float* fp = fp0 + r * 32;
-      const uint32_t mlo = wstart & (0xffffffffu >> (31 - r));
-      const int run_lo = mlo ? (i0 + 31 - __clz(mlo)) : prev_lo;
-      const uint32_t mhi = nextw & (0xffffffffu << r);
-      const int run_hi = mhi ? (i0 + __ffs(mhi)) : next_hi;          // exclusive
-      const int dl = i - run_lo;
-      const int dr = run_hi - 1 - i;
-      const float lo_term = (run_lo > 0 || border_lo) ? sq[dl + 1] : inf;
-      const float hi_term = (run_hi < n || border_hi) ? sq[dr + 1] : inf;
-      float best = fminf(*fp, fminf(lo_term, hi_term));
-      const int dmax = max(dl, dr);
-      float fd = 1.0f;
-      for (int d = 1; d <= dmax; ++d, fd += 1.0f) {
-        const float t = __fmul_rn(fd, fd);
-        if (!(__fmul_rn(w2, t) < best)) break;
-        if (d <= dl) best = fminf(best, __fmaf_rn(w2, t, fp[-d * 32]));
-        if (d <= dr) best = fminf(best, __fmaf_rn(w2, t, fp[d * 32]));
+    // (2) every other run that starts in this chunk: lower envelope over the whole run
+    uint32_t starts = wstart & ~single & (rows == 32 ? 0xffffffffu : ((1u << rows) - 1u));
+    if (starts) {
+      // first run start after this chunk (line end if none)
+      int next_hi = min(n, i0 + 32);
+      if (!ext) {
+        next_hi = n;
+        for (int cc = c + 1; cc < nchunks; ++cc) {
+          const uint32_t w = startw[(size_t)cc * TX + x];
+          if (w) { next_hi = min(n, (cc << 5) + __ffs(w) - 1); break; }
+        }
       }
-      if (Epilogue) best = finish_value(best, (wzero >> r) & 1u, flags);
-      *reinterpret_cast<float*>(op0 + (size_t)r * pitch) = best;
+      char* const line0 = reinterpret_cast<char*>(tf + x);
+      while (starts) {
+        const int r0 = __ffs(starts) - 1;
+        starts &= starts - 1u;
+        const int a = i0 + r0;
+        const uint32_t mhi = nextw & (0xffffffffu << r0);
+        const int b = mhi ? (i0 + __ffs(mhi)) : next_hi;              // exclusive
+        HullBits<TX> hb;
+        hb.own = hull_own + x; hb.in = hull_in + x; hb.ca = c;
+        envelope_run<TX, Epilogue>(fs + x, hb, a, b, w2, a > 0 || border_lo, b < n || border_hi, sq,
+                                   line0, pitch, (wzero >> r0) & 1u, flags);
+      }
     }
   }
 }

@@ -126,7 +126,8 @@ def test_long_axes(edt, oracle):
   col[17, 0] = 0
   assert_same(edt.edtsq(col, anisotropy=(3.0, 1.0)), oracle.edtsq(col, anisotropy=(3.0, 1.0)), "1x46342")
   rng = np.random.default_rng(11)
-  for shape in ((3, 5, 2500), (2500, 5, 3), (4, 2100)):
+  for shape in ((3, 5, 2500), (2500, 5, 3), (4, 2100), (40, 1100, 3), (3, 1100, 40), (9, 4096), (9, 4097),
+                (4096, 9), (2, 3000, 2)):
     lab = cases.random_volume(rng, shape, "blocks", np.uint16)
     lab[lab == 0] = 7        # long runs, no background: inf-rich without a border
     lab.flat[5] = 0
