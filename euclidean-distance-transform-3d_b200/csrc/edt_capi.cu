@@ -216,7 +216,7 @@ bool make_tile_map(CUtensorMap* map, float* f, const edtb200::LineGeom& g, int t
 // Shared memory of one tile of `tx` lines (see later_axis_tile_kernel).
 size_t tile_smem_bytes(int n, int tx, int rows_alloc) {
   const int nchunks = (n + 31) >> 5;
-  return (size_t)rows_alloc * tx * 4 + (size_t)nchunks * tx * 16 + (size_t)((n + 3) & ~1) * 4 + 16;
+  return (size_t)rows_alloc * tx * 4 + (size_t)nchunks * tx * 12 + (size_t)((n + 3) & ~1) * 4 + 16;
 }
 
 template <int Bytes, int TX>
@@ -268,22 +268,14 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
     const bool aligned = reinterpret_cast<uintptr_t>(f) % 16 == 0 && g.line_stride % 4 == 0 &&
                          (g.outer_count <= 1 || g.outer_stride % 4 == 0);
     // Tile width: 128-byte rows (TX = 32) keep DRAM pages and L2 lines whole and measured
-    // fastest whenever at least 2 CTAs fit per SM; narrower tiles only for long lines.
-    static const size_t budgets[3] = {75 * 1024, 113 * 1024, 0};   // 3, 2, 1 CTAs per SM
+    // fastest even at one CTA per SM; narrower tiles only when a 32-wide tile cannot fit.
     int tx = 0;
     for (int cand = 32; cand >= 8 && !tx; cand >>= 1) {
       const int nb = (g.n + 255) / 256;
       int br = (g.n + nb - 1) / nb;
       if (nb > 1) br = (br + 3) & ~3;
-      if (tile_smem_bytes(g.n, cand, br * nb) <= budgets[1]) tx = cand;
+      if (tile_smem_bytes(g.n, cand, br * nb) <= (size_t)dc.max_smem_optin) tx = cand;
     }
-    if (!tx) {
-      const int nb = (g.n + 255) / 256;
-      int br = (g.n + nb - 1) / nb;
-      if (nb > 1) br = (br + 3) & ~3;
-      if (tile_smem_bytes(g.n, 8, br * nb) <= (size_t)dc.max_smem_optin) tx = 8;
-    }
-    (void)budgets;
     if (tx) {
       const bool use_tma = aligned && g.inner_count >= tx;
       switch (tx) {

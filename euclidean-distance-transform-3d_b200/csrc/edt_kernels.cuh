@@ -352,7 +352,7 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
 //                         a 3-D tensor map of the volume; ragged tiles are zero-filled by the
 //                         hardware) while the threads work on the labels;
 //     startw[n/32][TX]    one 32-bit "a run of equal labels starts here" word per 32 rows;
-//     hull_own/in[n/32][TX]  lower-envelope membership bits (the scan's vertex stack, 1 bit/voxel);
+//     hullw[n/32][TX]     lower-envelope membership bits (the scan's vertex stack, 1 bit/voxel);
 //     sq[n+2]             w2*e^2, the closed-form border terms.
 // Thread (x = lane % TX, chunk = 32 consecutive rows) turns its label column into a run-start
 // word, then produces the outputs of the runs that START in its chunk:
@@ -417,101 +417,134 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-// Hull membership bits of one line: bit (pos & 31) of word (pos >> 5) says "pos is a vertex of
-// the lower envelope".  Two arrays keep writers apart without atomics: a run's bits go to
-// `own` for the rows of the chunk it starts in and to `in` for the rows of later chunks (at
-// most one run can enter a chunk from below, and the runs starting in a chunk are all
-// processed, one after the other, by that chunk's thread).
-template <int TX>
-struct HullBits {
-  uint32_t* own;   // &hull_own[0][x], row stride TX
-  uint32_t* in;    // &hull_in[0][x]
-  int ca;          // chunk in which the current run starts
-  __device__ __forceinline__ uint32_t load(int wi) const { return (wi == ca ? own : in)[wi * TX]; }
-  __device__ __forceinline__ void store(int wi, uint32_t v) const { (wi == ca ? own : in)[wi * TX] = v; }
-};
-
-// Smallest hull vertex position in (after, b), or -1.
-template <int TX>
-__device__ __forceinline__ int hull_next_vertex(const HullBits<TX> hb, int after, int b) {
-  const int pos = after + 1;
-  if (pos >= b) return -1;
-  const int wlast = (b - 1) >> 5;
-  int wi = pos >> 5;
-  uint32_t m = hb.load(wi) & (0xffffffffu << (pos & 31));
-  while (m == 0u) {
-    if (wi == wlast) return -1;
-    ++wi;
-    m = hb.load(wi);
-  }
-  const int v = (wi << 5) + __ffs(m) - 1;
-  return v < b ? v : -1;
+// ---- shared-memory accessors on 32-bit shared-window addresses ----
+// (explicit ld/st.shared: pointer arithmetic on generic pointers made the compiler rebuild the
+// shared-window base inside every loop iteration)
+// Plain loads are NOT volatile so that the compiler may schedule them freely; they are used only
+// for data that is immutable once the tile is staged, and every address they use is derived from
+// a token produced after the staging barrier (see `smem_token`), which keeps them below it.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// Volatile load for words that are rewritten while the kernel runs (the hull bits).
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// Zero that the compiler cannot see through, produced at this point of the program order.
+__device__ __forceinline__ uint32_t smem_token() {
+  uint32_t t;
+  asm volatile("mov.u32 %0, 0;" : "=r"(t) : : "memory");
+  return t;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
-// Lower envelope of the parabolas rooted at the finite samples of one run [a, b) of one line.
-//   fcol : &fs[0][x] (row stride TX floats)
-//   out  : byte address of the line's row 0 in global memory, `pitch` bytes between rows
-template <int TX, bool Epilogue>
-__device__ __forceinline__ void envelope_run(const float* __restrict__ fcol, HullBits<TX> hb, int a, int b,
-                                             float w2f, bool lo_border, bool hi_border,
-                                             const float* __restrict__ sq, char* __restrict__ out,
-                                             size_t pitch, bool background, int flags) {
-  const float inf = __int_as_float(0x7f800000);
-  const double w2 = (double)w2f;
-  const int wa = a >> 5;
-  const uint32_t amask = 0xffffffffu << (a & 31);
-
-  // ---- build: drop every vertex hidden by its neighbours ----
-  int cw = wa;                   // word currently held in `cur`
-  uint32_t cur = hb.load(wa);    // bits of earlier runs (positions < a) are left alone
-  int cnt = 0;                   // vertices on the hull
-  int q = 0, p = 0;              // top vertex and the one below it
-  double fq = 0.0;               // f[q]
-  double num = 0.0, den = 1.0;   // s(p,q) = num / (2*w2*den), kept as the pair (num, den)
-  for (int r = a; r < b; ++r) {
-    if ((r >> 5) != cw) { hb.store(cw, cur); cw = r >> 5; cur = 0u; }
-    const float frf = fcol[r * TX];
-    if (!(frf < inf)) continue;                       // +inf: not a site
-    const double fr = (double)frf;
-    double num_r = 0.0, den_r = 1.0;
-    while (cnt >= 1) {
-      den_r = (double)(r - q);
-      num_r = (fr - fq) + w2 * (den_r * (double)(r + q));
-      if (cnt == 1) break;                            // the bottom vertex is never dropped
-      if (num_r * den > num * den_r) break;           // s(q,r) > s(p,q): q stays
-      {                                               // drop q
-        const int wq = q >> 5;
-        const uint32_t bit = 1u << (q & 31);
-        if (wq == cw) cur &= ~bit; else hb.store(wq, hb.load(wq) & ~bit);
-      }
-      --cnt;
-      q = p;
-      fq = (double)fcol[q * TX];
-      if (cnt >= 2) {                                 // vertex below the new top
-        int wi = q >> 5;
-        uint32_t m = (wi == cw ? cur : hb.load(wi)) & ((1u << (q & 31)) - 1u);
-        if (wi == wa) m &= amask;
-        while (m == 0u) { --wi; m = hb.load(wi); if (wi == wa) m &= amask; }
-        p = (wi << 5) + 31 - __clz(m);
-        den = (double)(q - p);
-        num = (fq - (double)fcol[p * TX]) + w2 * (den * (double)(q + p));
-      }
-    }
-    cur |= 1u << (r & 31);
-    ++cnt;
-    p = q; num = num_r; den = den_r;
-    q = r; fq = fr;
+// ---- lower-envelope machinery shared by the three stages of later_axis_tile_kernel ----
+//
+// hullw[pos >> 5][x] bit (pos & 31) says "pos is a vertex of the lower envelope of its run".
+// All navigation is bounded by the run [a, b), because one word can hold bits of several runs.
+// One line of the tile: shared addresses of fs[0][x] and hullw[0][x]; rows are ROW bytes apart.
+template <int TX>
+struct TileLine {
+  static constexpr uint32_t ROW = TX * 4;
+  uint32_t f;      // &fs[0][x]
+  uint32_t hull;   // &hullw[0][x]
+  __device__ __forceinline__ float fval(int pos) const { return lds_f32(f + (uint32_t)pos * ROW); }
+  __device__ __forceinline__ uint32_t hword(int wi) const { return lds_u32_volatile(hull + (uint32_t)wi * ROW); }
+  __device__ __forceinline__ void drop(int pos) const {
+    const uint32_t at = hull + (uint32_t)(pos >> 5) * ROW;
+    sts_u32(at, lds_u32_volatile(at) & ~(1u << (pos & 31)));
   }
-  hb.store(cw, cur);
+};
 
-  // ---- read out: walk the hull, one fused multiply-add per candidate ----
-  int v = hull_next_vertex<TX>(hb, a - 1, b);
-  int v1 = (v >= 0) ? hull_next_vertex<TX>(hb, v, b) : -1;
-  float fv = inf, fv1 = inf, dv = 0.0f, dv1 = 0.0f;   // dv = (float)(i - v)
-  if (v >= 0) { fv = fcol[v * TX]; dv = (float)(a - v); }
-  if (v1 >= 0) { fv1 = fcol[v1 * TX]; dv1 = (float)(a - v1); }
-  char* dst = out + (size_t)a * pitch;
-  for (int i = a; i < b; ++i) {
+// Vertex m is hidden when the parabola of r overtakes it no later than m overtakes l:
+// s(m,r) <= s(l,m), compared by cross-multiplication in double (the reference divides in
+// double, src/edt.hpp:205-221; for integer-valued data both are exact).
+__device__ __forceinline__ bool vertex_hidden(int l, float fl, int m, float fm, int r, float fr, double w2) {
+  const double dml = (double)(m - l), drm = (double)(r - m);
+  const double nml = ((double)fm - (double)fl) + w2 * (dml * (double)(m + l));
+  const double nrm = ((double)fr - (double)fm) + w2 * (drm * (double)(r + m));
+  return nrm * dml <= nml * drm;
+}
+
+// Largest vertex v with a <= v < pos, or -1.
+template <int TX>
+__device__ __forceinline__ int prev_vertex(const TileLine<TX> ln, int pos, int a) {
+  if (pos <= a) return -1;
+  const int wa = a >> 5;
+  int wi = (pos - 1) >> 5;
+  uint32_t m = ln.hword(wi) & (0xffffffffu >> (31 - ((pos - 1) & 31)));
+  for (;;) {
+    if (wi == wa) m &= 0xffffffffu << (a & 31);
+    if (m) return (wi << 5) + 31 - __clz(m);
+    if (wi == wa) return -1;
+    --wi;
+    m = ln.hword(wi);
+  }
+}
+
+// Smallest vertex v with pos < v < b, or -1.
+template <int TX>
+__device__ __forceinline__ int next_vertex(const TileLine<TX> ln, int pos, int b) {
+  if (pos + 1 >= b) return -1;
+  const int wb = (b - 1) >> 5;
+  int wi = (pos + 1) >> 5;
+  uint32_t m = ln.hword(wi) & (0xffffffffu << ((pos + 1) & 31));
+  for (;;) {
+    if (wi == wb) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+    if (m) return (wi << 5) + __ffs(m) - 1;
+    if (wi == wb) return -1;
+    ++wi;
+    m = ln.hword(wi);
+  }
+}
+
+// Write the outputs of rows [lo, hi) of the run [a, b) by walking the (final) hull of the run.
+//   sq = shared address of the border-term table; line0 = byte address of row 0 in global memory.
+template <int TX, bool Epilogue>
+__device__ __forceinline__ void read_out(const TileLine<TX> ln, int lo, int hi, int a, int b, float w2f,
+                                         bool lo_border, bool hi_border, uint32_t sq,
+                                         char* __restrict__ line0, size_t pitch, bool background, int flags) {
+  const float inf = __int_as_float(0x7f800000);
+  // vertex that dominates row `lo`: start at the nearest vertex at or below lo (else the first one
+  // above), then descend along the hull -- at a fixed row the candidate values are unimodal.
+  int v = prev_vertex<TX>(ln, lo + 1, a);
+  if (v < 0) v = next_vertex<TX>(ln, lo, b);
+  float fv = inf, dv = 0.0f;
+  if (v >= 0) {
+    fv = ln.fval(v);
+    dv = (float)(lo - v);
+    float best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
+    for (;;) {
+      const int u = prev_vertex<TX>(ln, v, a);
+      if (u < 0) break;
+      const float fu = ln.fval(u);
+      const float du = (float)(lo - u);
+      const float cand = __fmaf_rn(w2f, __fmul_rn(du, du), fu);
+      if (!(cand < best)) break;
+      best = cand; v = u; fv = fu; dv = du;
+    }
+  }
+  int v1 = (v >= 0) ? next_vertex<TX>(ln, v, b) : -1;
+  float fv1 = inf, dv1 = 0.0f;
+  if (v1 >= 0) { fv1 = ln.fval(v1); dv1 = (float)(lo - v1); }
+  char* dst = line0 + (size_t)lo * pitch;
+  uint32_t sq_lo = sq + (uint32_t)(lo - a + 1) * 4u;     // sq[i - a + 1]
+  uint32_t sq_hi = sq + (uint32_t)(b - lo) * 4u;         // sq[b - i]
+  for (int i = lo; i < hi; ++i) {
     float best = inf;
     if (v >= 0) {
       best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
@@ -519,21 +552,105 @@ __device__ __forceinline__ void envelope_run(const float* __restrict__ fcol, Hul
         const float cand = __fmaf_rn(w2f, __fmul_rn(dv1, dv1), fv1);
         if (!(cand <= best)) break;
         best = cand; v = v1; fv = fv1; dv = dv1;
-        v1 = hull_next_vertex<TX>(hb, v1, b);
-        if (v1 >= 0) { fv1 = fcol[v1 * TX]; dv1 = (float)(i - v1); }
+        v1 = next_vertex<TX>(ln, v1, b);
+        if (v1 >= 0) { fv1 = ln.fval(v1); dv1 = (float)(i - v1); }
       }
       dv += 1.0f; dv1 += 1.0f;
     }
-    if (lo_border) best = fminf(best, sq[i - a + 1]);
-    if (hi_border) best = fminf(best, sq[b - i]);
+    if (lo_border) best = fminf(best, lds_f32(sq_lo));
+    if (hi_border) best = fminf(best, lds_f32(sq_hi));
+    sq_lo += 4u; sq_hi -= 4u;
     if (Epilogue) best = finish_value(best, background, flags);   // a run has one label
     *reinterpret_cast<float*>(dst) = best;
     dst += pitch;
   }
 }
 
+// Same for a run [sa, sb) that lies inside one 32-row chunk starting at row i0: the hull is the
+// register word `hb` (bit = row - i0), so navigation is a handful of bit operations.
+template <int TX, bool Epilogue>
+__device__ __forceinline__ void read_out_local(const TileLine<TX> ln, uint32_t hb, int i0, int sa, int sb,
+                                               float w2f, bool lo_border, bool hi_border, uint32_t sq,
+                                               char* __restrict__ line0, size_t pitch, bool background,
+                                               int flags) {
+  const float inf = __int_as_float(0x7f800000);
+  uint32_t left = hb & (0xffffffffu << (sa - i0));       // vertices of this run, bits relative to i0
+  if (sb - i0 < 32) left &= (1u << (sb - i0)) - 1u;
+  int v = -1, v1 = -1;
+  float fv = inf, fv1 = inf, dv = 0.0f, dv1 = 0.0f;
+  if (left) {
+    v = i0 + __ffs(left) - 1; left &= left - 1u;
+    fv = ln.fval(v); dv = (float)(sa - v);
+    if (left) { v1 = i0 + __ffs(left) - 1; left &= left - 1u; fv1 = ln.fval(v1); dv1 = (float)(sa - v1); }
+  }
+  char* dst = line0 + (size_t)sa * pitch;
+  uint32_t sq_lo = sq + 4u;                              // sq[i - sa + 1]
+  uint32_t sq_hi = sq + (uint32_t)(sb - sa) * 4u;        // sq[sb - i]
+  for (int i = sa; i < sb; ++i) {
+    float best = inf;
+    if (v >= 0) {
+      best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
+      while (v1 >= 0) {
+        const float cand = __fmaf_rn(w2f, __fmul_rn(dv1, dv1), fv1);
+        if (!(cand <= best)) break;
+        best = cand; v = v1; fv = fv1; dv = dv1;
+        if (left) { v1 = i0 + __ffs(left) - 1; left &= left - 1u; fv1 = ln.fval(v1); dv1 = (float)(i - v1); }
+        else v1 = -1;
+      }
+      dv += 1.0f; dv1 += 1.0f;
+    }
+    if (lo_border) best = fminf(best, lds_f32(sq_lo));
+    if (hi_border) best = fminf(best, lds_f32(sq_hi));
+    sq_lo += 4u; sq_hi -= 4u;
+    if (Epilogue) best = finish_value(best, background, flags);
+    *reinterpret_cast<float*>(dst) = best;
+    dst += pitch;
+  }
+}
+
+// Lower envelope of the finite samples of rows [sa, sb) (sb - o <= 32), as a bit mask relative
+// to row `o`: returns hb with the bits of the surviving vertices set (other bits untouched).
+// Classic stack scan with the stack kept as bits: top vertex q, the one below it p, and
+// (num, den) = numerator / denominator of s(p,q) so that each test is a cross-multiplication.
+template <int TX>
+__device__ __forceinline__ uint32_t build_hull(const TileLine<TX> ln, int o, int sa, int sb, double w2d,
+                                               uint32_t hb) {
+  const float inf = __int_as_float(0x7f800000);
+  const uint32_t segmask = 0xffffffffu << (sa - o);
+  int cnt = 0, q = 0, p = 0;
+  double qd = 0.0, fqd = 0.0, num = 0.0, den = 1.0;
+  double rd = (double)sa;
+  uint32_t fr_a = ln.f + (uint32_t)sa * TileLine<TX>::ROW;
+  for (int r = sa; r < sb; ++r, rd += 1.0, fr_a += TileLine<TX>::ROW) {
+    const float fr = lds_f32(fr_a);
+    if (!(fr < inf)) continue;                       // +inf: not a site
+    const double frd = (double)fr;
+    double den_r = rd - qd;
+    double num_r = (frd - fqd) + w2d * (den_r * (rd + qd));
+    while (cnt >= 2 && num_r * den <= num * den_r) {  // s(q,r) <= s(p,q): q is hidden
+      hb &= ~(1u << (q - o));
+      --cnt;
+      q = p; qd = (double)q; fqd = (double)ln.fval(q);
+      if (cnt >= 2) {
+        const uint32_t m = hb & segmask & ((1u << (q - o)) - 1u);
+        p = o + 31 - __clz(m);
+        const double pd = (double)p;
+        den = qd - pd;
+        num = (fqd - (double)ln.fval(p)) + w2d * (den * (qd + pd));
+      }
+      den_r = rd - qd;
+      num_r = (frd - fqd) + w2d * (den_r * (rd + qd));
+    }
+    hb |= 1u << (r - o);
+    ++cnt;
+    p = q; num = num_r; den = den_r;
+    q = r; qd = rd; fqd = frd;
+  }
+  return hb;
+}
+
 template <int Bytes, int TX, bool Epilogue, bool UseTMA>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 3)      // 3 CTAs of 512 threads per SM: at most 42 registers
 later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
                        const typename LabelOf<Bytes>::type* __restrict__ labels,
                        float* __restrict__ f, LineGeom g, TileBoxes tb, float w2,
@@ -541,17 +658,19 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   using LT = typename LabelOf<Bytes>::type;
   extern __shared__ __align__(128) unsigned char smem_tile[];
   constexpr int SUBS = 32 / TX;                       // chunks handled side by side by one warp
+  constexpr uint32_t ROW = TX * 4;                    // bytes between rows of fs / between words
 
   const int n = g.n;
   const int nchunks = (n + 31) >> 5;
   const int rows_alloc = UseTMA ? tb.box_rows * tb.nboxes : n;
-  float* fs = reinterpret_cast<float*>(smem_tile);                               // [rows_alloc][TX]
-  uint32_t* startw = reinterpret_cast<uint32_t*>(fs + (size_t)rows_alloc * TX);  // [nchunks][TX]
-  uint32_t* zerow = startw + (size_t)nchunks * TX;                               // [nchunks][TX]
-  uint32_t* hull_own = zerow + (size_t)nchunks * TX;                             // [nchunks][TX]
-  uint32_t* hull_in = hull_own + (size_t)nchunks * TX;                           // [nchunks][TX]
-  float* sq = reinterpret_cast<float*>(hull_in + (size_t)nchunks * TX);          // [n + 2]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sq + ((n + 2 + 1) & ~1));
+  // shared-memory map (byte addresses in the shared window)
+  const uint32_t fs_a = smem_addr(smem_tile);                           // float [rows_alloc][TX]
+  const uint32_t startw_a = fs_a + (uint32_t)rows_alloc * ROW;          // u32   [nchunks][TX]
+  const uint32_t zerow_a = startw_a + (uint32_t)nchunks * ROW;          // u32   [nchunks][TX]
+  const uint32_t hullw_a = zerow_a + (uint32_t)nchunks * ROW;           // u32   [nchunks][TX]
+  const uint32_t sq_a = hullw_a + (uint32_t)nchunks * ROW;              // float [n + 2]
+  const uint32_t bar_a = sq_a + (uint32_t)((n + 2 + 1) & ~1) * 4u;      // mbarrier
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_tile + (bar_a - fs_a));
 
   const int lane = threadIdx.x & 31;
   const int x = lane & (TX - 1);
@@ -566,18 +685,21 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   const LT* __restrict__ tl = labels + (outer * g.outer_stride + inner0);
   float* __restrict__ tf = f + (outer * g.outer_stride + inner0);
   const uint32_t ls = (uint32_t)g.line_stride;
+  const size_t pitch = (size_t)ls * sizeof(float);
+  const float inf = __int_as_float(0x7f800000);
+  const double w2d = (double)w2;
 
   if (UseTMA && threadIdx.x == 0) {
     mbar_init(bar, 1);
-    mbar_expect_tx(bar, (unsigned)rows_alloc * (unsigned)(TX * sizeof(float)));
+    mbar_expect_tx(bar, (unsigned)rows_alloc * ROW);
     for (int bx = 0; bx < tb.nboxes; ++bx)
-      tma_load_3d(fs + (size_t)bx * tb.box_rows * TX, &fmap, (int)inner0, bx * tb.box_rows, (int)outer, bar);
+      tma_load_3d(smem_tile + (size_t)bx * tb.box_rows * ROW, &fmap, (int)inner0, bx * tb.box_rows, (int)outer, bar);
   }
 
-  // ---- labels -> run-start / background words; border-term table; (plain loads of f) ----
+  // ============ stage 0: labels -> run-start / background words; border-term table ============
   for (int i = threadIdx.x; i < n + 2; i += blockDim.x) {
     const float e = (float)i;
-    sq[i] = __fmul_rn(w2, __fmul_rn(e, e));
+    sts_f32(sq_a + (uint32_t)i * 4u, __fmul_rn(w2, __fmul_rn(e, e)));
   }
   for (int c = chunk0; c < nchunks; c += chunk_step) {
     const int i0 = c << 5;
@@ -585,11 +707,12 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
     if (live) {
       uint32_t idx = (uint32_t)i0 * ls + (uint32_t)x;
       LT prev = (i0 > 0) ? tl[idx - ls] : (LT)0;
+      uint32_t fdst = fs_a + (uint32_t)i0 * ROW + (uint32_t)x * 4u;
       if (i0 + 32 <= n) {
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
           const LT here = tl[idx];
-          if (!UseTMA) fs[(size_t)(i0 + r) * TX + x] = tf[idx];
+          if (!UseTMA) sts_f32(fdst + r * ROW, tf[idx]);
           idx += ls;
           if (here != prev) wstart |= (1u << r);
           if (Epilogue && here == 0) wzero |= (1u << r);
@@ -598,7 +721,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       } else {
         for (int r = 0; r < n - i0; ++r) {
           const LT here = tl[idx];
-          if (!UseTMA) fs[(size_t)(i0 + r) * TX + x] = tf[idx];
+          if (!UseTMA) sts_f32(fdst + r * ROW, tf[idx]);
           idx += ls;
           if (here != prev) wstart |= (1u << r);
           if (Epilogue && here == 0) wzero |= (1u << r);
@@ -608,73 +731,195 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       }
       if (i0 == 0) wstart |= 1u;           // a run starts at row 0 by definition
     }
-    startw[(size_t)c * TX + x] = wstart;
-    if (Epilogue) zerow[(size_t)c * TX + x] = wzero;
-    hull_own[(size_t)c * TX + x] = 0u;
-    hull_in[(size_t)c * TX + x] = 0u;
+    sts_u32(startw_a + (uint32_t)c * ROW + (uint32_t)x * 4u, wstart);
+    if (Epilogue) sts_u32(zerow_a + (uint32_t)c * ROW + (uint32_t)x * 4u, wzero);
   }
   __syncthreads();         // words, table (and plain-loaded tile) visible; orders the mbarrier init
   if (UseTMA) mbar_wait(bar, 0);       // float tile has landed
-  if (!live) return;
 
-  for (int c = chunk0; c < nchunks; c += chunk_step) {
-    const int i0 = c << 5;
-    const int rows = min(32, n - i0);
-    const uint32_t wstart = startw[(size_t)c * TX + x];
-    const uint32_t wzero = Epilogue ? zerow[(size_t)c * TX + x] : 0u;
-    // bit r of `nextw`: a run starts at row i0 + r + 1 (the line end counts as a start)
-    uint32_t ext = 1u;
-    if (i0 + 32 < n) ext = startw[(size_t)(c + 1) * TX + x] & 1u;
-    const uint32_t nextw = (wstart >> 1) | (ext << 31);
-    uint32_t single = wstart & nextw;                    // runs of length one
-    if (!border_lo && c == 0) single &= ~1u;             // rows lacking a border term go the long way
-    if (!border_hi && i0 + 32 >= n) single &= ~(1u << (n - 1 - i0));
+  // every shared address used from here on carries the token, so no (non-volatile) load of the
+  // staged tile can be scheduled above the barrier / the TMA completion wait
+  const uint32_t tok = smem_token();
+  TileLine<TX> ln;
+  ln.f = fs_a + (uint32_t)x * 4u + tok;
+  ln.hull = hullw_a + (uint32_t)x * 4u + tok;
+  const uint32_t startcol = startw_a + (uint32_t)x * 4u + tok;
+  const uint32_t zerocol = zerow_a + (uint32_t)x * 4u + tok;
+  const uint32_t sq_t = sq_a + tok;
+  char* const line0 = reinterpret_cast<char*>(tf + x);
 
-    const float* fp0 = fs + (size_t)i0 * TX + x;
-    char* const op0 = reinterpret_cast<char*>(tf + ((uint32_t)i0 * ls + (uint32_t)x));
-    const size_t pitch = (size_t)ls * sizeof(float);
+  // ============ stage 1: runs of length one; hulls of every other run, chunk by chunk ============
+  int crossing = 0;                                        // does any of my chunks hold an open segment?
+  if (live) {
+    for (int c = chunk0; c < nchunks; c += chunk_step) {
+      const int i0 = c << 5;
+      const int rows = min(32, n - i0);
+      const uint32_t rowmask = rows == 32 ? 0xffffffffu : ((1u << rows) - 1u);
+      const uint32_t wstart = lds_u32(startcol + (uint32_t)c * ROW);
+      const uint32_t wzero = Epilogue ? lds_u32(zerocol + (uint32_t)c * ROW) : 0u;
+      // bit r of `nextw`: a run starts at row i0 + r + 1 (the line end counts as a start)
+      uint32_t ext = 1u;
+      if (i0 + 32 < n) ext = lds_u32(startcol + (uint32_t)(c + 1) * ROW) & 1u;
+      const uint32_t nextw = (wstart >> 1) | (ext << 31);
+      uint32_t single = wstart & nextw;                    // runs of length one
+      if (!border_lo && c == 0) single &= ~1u;             // rows lacking a border term go the long way
+      if (!border_hi && i0 + 32 >= n) single &= ~(1u << (n - 1 - i0));
 
-    // (1) runs of length one: min(f, w2); value computed unconditionally, store predicated
-    if (rows == 32) {
-      char* op = op0;
+      // (1a) runs of length one: min(f, w2); value computed unconditionally, store predicated
+      const uint32_t fp0 = ln.f + (uint32_t)i0 * ROW;
+      char* const op0 = line0 + (size_t)i0 * pitch;
+      if (rows == 32) {
+        char* op = op0;
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        float v = fminf(fp0[r * TX], w2);
-        if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
-        if (single & (1u << r)) *reinterpret_cast<float*>(op) = v;
-        op += pitch;
-      }
-    } else {
-      for (int r = 0; r < rows; ++r) {
-        float v = fminf(fp0[r * TX], w2);
-        if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
-        if (single & (1u << r)) *reinterpret_cast<float*>(op0 + (size_t)r * pitch) = v;
-      }
-    }
-
-    // (2) every other run that starts in this chunk: lower envelope over the whole run
-    uint32_t starts = wstart & ~single & (rows == 32 ? 0xffffffffu : ((1u << rows) - 1u));
-    if (starts) {
-      // first run start after this chunk (line end if none)
-      int next_hi = min(n, i0 + 32);
-      if (!ext) {
-        next_hi = n;
-        for (int cc = c + 1; cc < nchunks; ++cc) {
-          const uint32_t w = startw[(size_t)cc * TX + x];
-          if (w) { next_hi = min(n, (cc << 5) + __ffs(w) - 1); break; }
+        for (int r = 0; r < 32; ++r) {
+          float v = fminf(lds_f32(fp0 + r * ROW), w2);
+          if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
+          if (single & (1u << r)) *reinterpret_cast<float*>(op) = v;
+          op += pitch;
+        }
+      } else {
+        for (int r = 0; r < rows; ++r) {
+          float v = fminf(lds_f32(fp0 + r * ROW), w2);
+          if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
+          if (single & (1u << r)) *reinterpret_cast<float*>(op0 + (size_t)r * pitch) = v;
         }
       }
-      char* const line0 = reinterpret_cast<char*>(tf + x);
-      while (starts) {
-        const int r0 = __ffs(starts) - 1;
-        starts &= starts - 1u;
-        const int a = i0 + r0;
+
+      // (1b) every other run that starts in this chunk.  Runs of at most 32 rows -- even when they
+      // spill into the next chunk -- are finished here with their hull in a register (bits relative
+      // to the run start).  Longer runs only get the hull of their rows in this chunk, recorded in
+      // hullw (bits relative to i0), and are stitched and read out in stages 2 and 3.
+      uint32_t hb = 0u;
+      const uint32_t todo = wstart & rowmask & ~single;
+      int next_start = -1;                                 // first run start after this chunk (lazy)
+      for (uint32_t rest = todo; rest;) {
+        const int r0 = __ffs(rest) - 1;
+        rest &= rest - 1u;
         const uint32_t mhi = nextw & (0xffffffffu << r0);
-        const int b = mhi ? (i0 + __ffs(mhi)) : next_hi;              // exclusive
-        HullBits<TX> hb;
-        hb.own = hull_own + x; hb.in = hull_in + x; hb.ca = c;
-        envelope_run<TX, Epilogue>(fs + x, hb, a, b, w2, a > 0 || border_lo, b < n || border_hi, sq,
-                                   line0, pitch, (wzero >> r0) & 1u, flags);
+        const int sa = i0 + r0;
+        int sb;
+        if (mhi) {
+          sb = i0 + __ffs(mhi);
+        } else {                                           // the run leaves this chunk: where does it end?
+          if (next_start < 0) {
+            next_start = n;
+            for (int cc = c + 1; cc < nchunks; ++cc) {
+              const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+              if (w) { next_start = min(n, (cc << 5) + __ffs(w) - 1); break; }
+            }
+          }
+          sb = next_start;
+        }
+        if (sb - sa <= 32) {
+          const uint32_t lb = build_hull<TX>(ln, sa, sa, sb, w2d, 0u);
+          read_out_local<TX, Epilogue>(ln, lb, sa, sa, sb, w2, sa > 0 || border_lo, sb < n || border_hi, sq_t,
+                                       line0, pitch, (wzero >> r0) & 1u, flags);
+        } else {
+          hb = build_hull<TX>(ln, i0, sa, i0 + 32, w2d, hb);
+          crossing = 1;
+        }
+      }
+      // rows of a long run that entered from the chunk below (short ones were finished by their owner)
+      if (!(wstart & 1u)) {
+        int a_lo = 0;
+        for (int cc = c - 1; cc >= 0; --cc) {
+          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+          if (w) { a_lo = (cc << 5) + 31 - __clz(w); break; }
+        }
+        const uint32_t wreal = wstart & rowmask;
+        int b_run;
+        if (wreal) b_run = i0 + __ffs(wreal) - 1;
+        else if (!ext) {
+          if (next_start < 0) {
+            next_start = n;
+            for (int cc = c + 1; cc < nchunks; ++cc) {
+              const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+              if (w) { next_start = min(n, (cc << 5) + __ffs(w) - 1); break; }
+            }
+          }
+          b_run = next_start;
+        } else b_run = min(n, i0 + 32);
+        if (b_run - a_lo > 32) {
+          hb = build_hull<TX>(ln, i0, i0, min(b_run, i0 + rows), w2d, hb);
+          crossing = 1;
+        }
+      }
+      sts_u32(ln.hull + (uint32_t)c * ROW, hb);
+    }
+  }
+  if (!__syncthreads_or(crossing)) return;                 // every run was finished inside its chunk
+
+  // ============ stage 2: stitch the hulls of runs that cross chunk boundaries ============
+  // One thread per line walks the boundaries bottom-up.  Left of a boundary stands the final
+  // hull of everything below (A), right of it the local hull of the next chunk's first segment
+  // (B); all of A lies left of all of B, so their union's hull is a prefix of A plus a suffix of
+  // B: drop A's top while it is hidden by (the vertex below it, B's first), drop B's first while
+  // it is hidden by (A's top, B's second), until neither applies.
+  if (live && threadIdx.x < TX) {
+    int a = 0;                                             // start of the run open at the boundary
+    for (int c = 1; c < nchunks; ++c) {
+      const int i0 = c << 5;
+      const uint32_t wprev = lds_u32(startcol + (uint32_t)(c - 1) * ROW);
+      if (wprev) a = ((c - 1) << 5) + 31 - __clz(wprev);
+      const uint32_t wc = lds_u32(startcol + (uint32_t)c * ROW);
+      if (wc & 1u) continue;                               // a run starts exactly here: nothing crosses
+      const int sb = wc ? (i0 + __ffs(wc) - 1) : min(n, i0 + 32);
+      for (;;) {
+        const int av = prev_vertex<TX>(ln, i0, a);
+        if (av < 0) break;
+        const int bv = next_vertex<TX>(ln, i0 - 1, sb);
+        if (bv < 0) break;
+        const float fa = ln.fval(av), fb = ln.fval(bv);
+        const int ap = prev_vertex<TX>(ln, av, a);
+        if (ap >= 0 && vertex_hidden(ap, ln.fval(ap), av, fa, bv, fb, w2d)) { ln.drop(av); continue; }
+        const int bn = next_vertex<TX>(ln, bv, sb);
+        if (bn >= 0 && vertex_hidden(av, fa, bv, fb, bn, ln.fval(bn), w2d)) { ln.drop(bv); continue; }
+        break;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ============ stage 3: outputs of the run segments that cross chunk boundaries ============
+  if (live) {
+    for (int c = chunk0; c < nchunks; c += chunk_step) {
+      const int i0 = c << 5;
+      const int rows = min(32, n - i0);
+      const uint32_t wstart = lds_u32(startcol + (uint32_t)c * ROW);
+      const uint32_t wzero = Epilogue ? lds_u32(zerocol + (uint32_t)c * ROW) : 0u;
+      const bool open_lo = !(wstart & 1u);                              // only possible for c > 0
+      bool open_hi = false;
+      if (i0 + 32 < n) open_hi = !(lds_u32(startcol + (uint32_t)(c + 1) * ROW) & 1u);
+      if (!open_lo && !open_hi) continue;
+      const uint32_t wreal = wstart & (rows == 32 ? 0xffffffffu : ((1u << rows) - 1u));
+
+      int a_lo = 0, b_hi = min(n, i0 + 32);
+      if (open_lo) {                                                    // run start below this chunk
+        for (int cc = c - 1; cc >= 0; --cc) {
+          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+          if (w) { a_lo = (cc << 5) + 31 - __clz(w); break; }
+        }
+      }
+      if (open_hi) {                                                    // run end above this chunk
+        b_hi = n;
+        for (int cc = c + 1; cc < nchunks; ++cc) {
+          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+          if (w) { b_hi = min(n, (cc << 5) + __ffs(w) - 1); break; }
+        }
+      }
+      if (open_lo) {
+        const int hi = wreal ? (i0 + __ffs(wreal) - 1) : (i0 + rows);   // rows of this chunk in the run
+        const int b = wreal ? hi : b_hi;
+        if (b - a_lo > 32)                                              // short runs were finished in stage 1
+          read_out<TX, Epilogue>(ln, i0, hi, a_lo, b, w2, a_lo > 0 || border_lo, b < n || border_hi, sq_t,
+                                 line0, pitch, wzero & 1u, flags);
+      }
+      if (open_hi && wreal) {                                           // a run starting here and leaving above
+        const int r0 = 31 - __clz(wreal);
+        const int lo = i0 + r0;
+        if (b_hi - lo > 32)
+          read_out<TX, Epilogue>(ln, lo, i0 + 32, lo, b_hi, w2, lo > 0 || border_lo, b_hi < n || border_hi, sq_t,
+                                 line0, pitch, (wzero >> r0) & 1u, flags);
       }
     }
   }
