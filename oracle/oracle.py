@@ -40,6 +40,11 @@ def _lib():
     lib.oracle_edtsq.restype = ctypes.c_int
     lib.oracle_bruteforce_edtsq.argtypes = lib.oracle_edtsq.argtypes
     lib.oracle_bruteforce_edtsq.restype = ctypes.c_int
+    lib.oracle_pass_first.argtypes = [vp, ctypes.c_int, i64, i64, i64, f32, ctypes.c_int, vp]
+    lib.oracle_pass_first.restype = ctypes.c_int
+    lib.oracle_pass_later.argtypes = [vp, ctypes.c_int, ctypes.c_int, i64, i64, i64, f32, ctypes.c_int,
+                                      ctypes.c_int, vp]
+    lib.oracle_pass_later.restype = ctypes.c_int
     _LIB = lib
   return _LIB
 
@@ -152,3 +157,25 @@ def sdfsq(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=Non
 def bruteforce_edtsq(data, anisotropy=None, black_border=False):
   """O(N^2) evaluation of the definition; tiny volumes only."""
   return _run(_lib().oracle_bruteforce_edtsq, data, anisotropy, black_border)
+
+
+def pass_first(labels_zyx, wx, black_border):
+  """First-axis pass of a C-ordered (z, y, x) integer volume -> float32 (z, y, x)."""
+  lab = np.ascontiguousarray(labels_zyx)
+  sz, sy, sx = lab.shape
+  out = np.zeros(lab.shape, dtype=np.float32)
+  rc = _lib().oracle_pass_first(lab.ctypes.data, lab.dtype.itemsize, sx, sy, sz, float(wx),
+                                int(bool(black_border)), out.ctypes.data)
+  assert rc == 0
+  return out
+
+
+def pass_later(labels_zyx, f_zyx, axis, w, border_lo, border_hi):
+  """One envelope pass (axis 1 = y, 2 = z) of C-ordered (z, y, x) arrays, in place on f_zyx."""
+  lab = np.ascontiguousarray(labels_zyx)
+  assert f_zyx.flags.c_contiguous and f_zyx.dtype == np.float32
+  sz, sy, sx = lab.shape
+  rc = _lib().oracle_pass_later(lab.ctypes.data, lab.dtype.itemsize, int(axis), sx, sy, sz, float(w),
+                                int(bool(border_lo)), int(bool(border_hi)), f_zyx.ctypes.data)
+  assert rc == 0
+  return f_zyx

@@ -305,3 +305,45 @@ def test_blocks_256_vs_oracle(edt, oracle):
     assert_same(edt.edtsq(lab, anisotropy=(1, 1, 1), black_border=bb),
                 oracle.edtsq(lab, anisotropy=(1, 1, 1), black_border=bb), ("blocks256", bb))
   assert_same(edt.sdf(lab, anisotropy=(4, 4, 40)), oracle.sdf(lab, anisotropy=(4, 4, 40)), "blocks256 sdf")
+
+
+def test_cpp_shim_header(edt, oracle, tmp_path):
+  """include/edt.hpp: edt::edt<T> / edt::edtsq<T> with the reference's C++ signature
+  (src/edt.hpp:836-844, 907-922), compiled with g++ against libedt_b200.so."""
+  import shutil
+  import subprocess
+  if shutil.which("g++") is None:
+    pytest.skip("no g++")
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  src = tmp_path / "shim.cpp"
+  src.write_text(r'''
+#include "edt.hpp"
+#include <cstdio>
+#include <cstdlib>
+int main(int argc, char** argv) {
+  const int sx = 19, sy = 11, sz = 7;
+  std::vector<uint16_t> lab(sx * sy * sz);
+  FILE* fi = fopen(argv[1], "rb"); if (!fi || fread(lab.data(), 2, lab.size(), fi) != lab.size()) return 2; fclose(fi);
+  float* a = edt::edtsq<uint16_t>(lab.data(), sx, sy, sz, 2.f, 3.f, 5.f, true);
+  float* b = edt::edt<uint16_t>(lab.data(), sx, sy, sz, 2.f, 3.f, 5.f, false, 4);
+  std::vector<float> c(lab.size());
+  float* cret = edt::edtsq<uint16_t>(lab.data(), sx, sy, sz, 2.f, 3.f, 5.f, true, 1, c.data());
+  if (cret != c.data()) return 3;
+  FILE* fo = fopen(argv[2], "wb");
+  fwrite(a, 4, lab.size(), fo); fwrite(b, 4, lab.size(), fo); fwrite(c.data(), 4, lab.size(), fo); fclose(fo);
+  delete[] a; delete[] b;
+  return 0;
+}
+''')
+  exe = tmp_path / "shim"
+  libdir = os.path.dirname(edt.library_path())
+  subprocess.run(["g++", "-std=c++17", "-I", os.path.join(root, "include"), str(src), "-L", libdir,
+                  "-ledt_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+  rng = np.random.default_rng(21)
+  lab = np.asfortranarray(rng.integers(0, 4, (19, 11, 7)).astype(np.uint16))      # x fastest
+  (tmp_path / "in.bin").write_bytes(lab.tobytes(order="F"))
+  subprocess.run([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], check=True)
+  out = np.fromfile(tmp_path / "out.bin", dtype=np.float32).reshape(3, -1)
+  sq = oracle.edtsq(lab, anisotropy=(2, 3, 5), black_border=True).ravel(order="F")
+  assert np.array_equal(out[0], sq) and np.array_equal(out[2], sq)
+  assert np.array_equal(out[1], oracle.edt(lab, anisotropy=(2, 3, 5), black_border=False).ravel(order="F"))
