@@ -245,7 +245,7 @@ def ours(args):
     result = {}
     def step(events=None):
       result["out"] = ed.slab_transform(labels_dev, (ANISOTROPY[2], ANISOTROPY[1], ANISOTROPY[0]), False,
-                                        passes=passes)
+                                        passes=passes, info=result)
 
   for _ in range(max(3, args.warmup)):
     step()
@@ -279,7 +279,9 @@ def ours(args):
     roofline = {"bound": "hbm", "kernel": "whole slab step (3 passes + Z-slab<->Y-slab exchange)",
                 "achieved": alg / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg / (ms_per_step * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
-                "nvlink_bytes_per_gpu_per_step": int(nvox * (LABEL_BYTES + 8) * (world - 1) / world)}
+                "nvlink_bytes_per_gpu_per_step": (2 * 512 * 512 * (32 * 4 + LABEL_BYTES + 1)
+                                                  if result.get("method") == "halo"
+                                                  else int(nvox * (LABEL_BYTES + 8) * (world - 1) / world))}
     e2e_steps = max(2, min(args.steps, 5))
     hl_t, ho_t = labels_host, out_host
     def e2e_once():
@@ -307,10 +309,12 @@ def ours(args):
         "dtype": "f32 (u32 labels)", "data": "synthetic",
         "config": {"workload": "edtsq 512x512x%d uint32 iid-random labels 0..255, anisotropy (1,1,1), "
                                "Z-slab split, one 512^3 slab per GPU (BASELINE.json configs[4] geometry)" % (512 * world),
-                   "parallelism": "z-slab x%d; X,Y passes local; Z pass via Z-slab<->Y-slab all-to-all (NCCL p2p group)" % world,
+                   "parallelism": "z-slab x%d; X,Y passes local; Z pass local + one neighbour halo exchange (NCCL p2p group) "
+                                  "and face fix-up; method used: %s" % (world, result.get("method")),
                    "l2": "inputs (1 GiB per rank per step) larger than L2; no flush needed",
                    "timing": "CUDA events on the launch stream, max over ranks"},
-        "roofline": roofline, "e2e": e2e, "gpu_launches": 3 * args.steps, "clocks": clocks,
+        "roofline": roofline, "e2e": e2e, "gpu_launches": (7 if result.get("method") == "halo" else 3) * args.steps,
+        "clocks": clocks,
       }
       print(json.dumps(line), flush=True)
     dist.destroy_process_group()

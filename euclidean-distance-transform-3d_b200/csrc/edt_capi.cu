@@ -493,6 +493,62 @@ int edtb200_pass_later(const void* labels_dev, int label_bytes, int axis, int64_
                         *dc, static_cast<cudaStream_t>(stream));
 }
 
+int edtb200_slab_face_runs(const void* labels_dev, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
+                           int high_face, int halo, int flags, unsigned char* m_dev, int* overflow_dev,
+                           int device, void* stream_v) {
+  int rc = check_dims(label_bytes, 3, sx, sy, sz);
+  if (rc) return rc;
+  if (halo < 1 || halo > 254) return fail(EDTB200_EINVAL, "halo must be in 1..254");
+  if (sx * sy * sz == 0) return 0;
+  if (!labels_dev || !m_dev || !overflow_dev) return fail(EDTB200_EINVAL, "null pointer");
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceCache* dc = nullptr;
+  rc = probe(device, &dc);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int64_t plane = sx * sy;
+  const unsigned blocks = (unsigned)((plane + 255) / 256);
+  const int zl = (flags & EDTB200_SIGNED) ? 1 : 0;
+  using namespace edtb200;
+  switch (label_bytes) {
+    case 1: face_runs_kernel<1><<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(labels_dev), plane, (int)sz, high_face, halo, zl, m_dev, overflow_dev); break;
+    case 2: face_runs_kernel<2><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(labels_dev), plane, (int)sz, high_face, halo, zl, m_dev, overflow_dev); break;
+    case 4: face_runs_kernel<4><<<blocks, 256, 0, stream>>>(static_cast<const uint32_t*>(labels_dev), plane, (int)sz, high_face, halo, zl, m_dev, overflow_dev); break;
+    default: face_runs_kernel<8><<<blocks, 256, 0, stream>>>(static_cast<const uint64_t*>(labels_dev), plane, (int)sz, high_face, halo, zl, m_dev, overflow_dev); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int edtb200_slab_face_fixup(const void* labels_dev, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
+                            int high_face, int halo, float wz, int flags, const void* nb_label_dev,
+                            const unsigned char* nb_m_dev, const float* nb_f_dev, float* f_dev, int device,
+                            void* stream_v) {
+  int rc = check_dims(label_bytes, 3, sx, sy, sz);
+  if (rc) return rc;
+  if (halo < 1 || halo > 254) return fail(EDTB200_EINVAL, "halo must be in 1..254");
+  if (sx * sy * sz == 0) return 0;
+  if (!labels_dev || !nb_label_dev || !nb_m_dev || !nb_f_dev || !f_dev) return fail(EDTB200_EINVAL, "null pointer");
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceCache* dc = nullptr;
+  rc = probe(device, &dc);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int64_t plane = sx * sy;
+  const unsigned blocks = (unsigned)((plane + 255) / 256);
+  using namespace edtb200;
+  const int kflags = ((flags & EDTB200_SQRT) ? kSqrt : 0) | ((flags & EDTB200_SIGNED) ? (kNegate | kZeroLabel) : 0);
+  const float w2 = wz * wz;
+  switch (label_bytes) {
+    case 1: face_fixup_kernel<1><<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(labels_dev), f_dev, plane, (int)sz, high_face, halo, w2, static_cast<const uint8_t*>(nb_label_dev), nb_m_dev, nb_f_dev, kflags); break;
+    case 2: face_fixup_kernel<2><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(labels_dev), f_dev, plane, (int)sz, high_face, halo, w2, static_cast<const uint16_t*>(nb_label_dev), nb_m_dev, nb_f_dev, kflags); break;
+    case 4: face_fixup_kernel<4><<<blocks, 256, 0, stream>>>(static_cast<const uint32_t*>(labels_dev), f_dev, plane, (int)sz, high_face, halo, w2, static_cast<const uint32_t*>(nb_label_dev), nb_m_dev, nb_f_dev, kflags); break;
+    default: face_fixup_kernel<8><<<blocks, 256, 0, stream>>>(static_cast<const uint64_t*>(labels_dev), f_dev, plane, (int)sz, high_face, halo, w2, static_cast<const uint64_t*>(nb_label_dev), nb_m_dev, nb_f_dev, kflags); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int edtb200_release(void) {
   std::lock_guard<std::mutex> lock(g_mutex);
   int count = 0;

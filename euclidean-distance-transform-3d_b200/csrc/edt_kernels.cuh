@@ -980,4 +980,77 @@ later_axis_long_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Z-slab decomposition across GPUs (see distributed.py): the third-axis pass of a slab is run
+// with its interior faces OPEN (no border term), and the voxels of the neighbouring slab are
+// folded in afterwards as extra candidates for the runs that touch the face:
+//   * neighbour label differs: the face is a run border -> one zero-height site at distance 1;
+//   * neighbour label equal  : the neighbour's part of the run (m <= H rows, it must end inside
+//     the neighbour's slab) contributes its rows as sites, plus the zero-height site behind it.
+// Every such site lies outside the slab, so against the slab-local envelope its parabola only
+// gets worse (by at least 2*w2 per row) as rows move away from the face: the walk along a
+// column stops at the first row where no outside site improves the value.
+// Values are compared after the pass's epilogue: sqrt is monotone and the sign of a run is
+// fixed, so min() commutes with both.
+// ---------------------------------------------------------------------------------------
+
+// m[q] = length of the run of equal labels that touches the face (capped at H + 1 = "too long"),
+// for every line q of the sx*sy plane; *overflow is raised if any foreground run is too long.
+template <int Bytes>
+__global__ void __launch_bounds__(256)
+face_runs_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, int64_t plane, int nz, int high_face,
+                 int H, int zero_is_label, uint8_t* __restrict__ m_out, int* __restrict__ overflow) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= plane) return;
+  const int64_t row0 = high_face ? (int64_t)(nz - 1) : 0;
+  const int64_t step = high_face ? -1 : 1;
+  const auto lab0 = labels[row0 * plane + q];
+  int m = 1;
+  const int limit = min(nz, H + 1);
+  while (m < limit && labels[(row0 + step * m) * plane + q] == lab0) ++m;
+  if (m > H || m >= nz) {                 // runs that are too long, or that span the whole slab
+    m = H + 1;
+    if (lab0 != 0 || zero_is_label) *overflow = 1;
+  }
+  m_out[q] = (uint8_t)m;
+}
+
+// Fold the neighbour's sites into the rows of this slab that belong to face-touching runs.
+//   nb_label : the neighbour's face plane of labels        nb_m : its face_runs_kernel output
+//   nb_f     : H planes of the neighbour's distances AFTER its second-axis pass, in the
+//              neighbour's own z order (for the low face these are its LAST H planes)
+template <int Bytes>
+__global__ void __launch_bounds__(256)
+face_fixup_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, float* __restrict__ f,
+                  int64_t plane, int nz, int high_face, int H, float w2,
+                  const typename LabelOf<Bytes>::type* __restrict__ nb_label,
+                  const uint8_t* __restrict__ nb_m, const float* __restrict__ nb_f, int flags) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= plane) return;
+  const int64_t row0 = high_face ? (int64_t)(nz - 1) : 0;
+  const int64_t step = high_face ? -1 : 1;
+  const auto lab0 = labels[row0 * plane + q];
+  const bool background = lab0 == 0;
+  if (background && !(flags & kZeroLabel)) return;            // plain EDT: background stays 0
+  const bool same = nb_label[q] == lab0;
+  const int m = same ? (int)nb_m[q] : 0;                      // neighbour rows of this run (<= H)
+  const bool negative = (flags & kNegate) && background;
+  for (int j = 0; j < nz; ++j) {
+    const int64_t at = (row0 + step * j) * plane + q;
+    if (j > 0 && labels[at] != lab0) break;                   // end of the run inside this slab
+    // best outside site for row j: neighbour rows r = 0..m-1 at distance j + 1 + r, then the
+    // zero-height site behind them at distance j + 1 + m
+    float best = parabola_at(w2, j + 1 + m, 0.0f);
+    for (int r = 0; r < m; ++r) {
+      const int64_t src = (high_face ? (int64_t)r : (int64_t)(H - 1 - r)) * plane + q;
+      best = fminf(best, parabola_at(w2, j + 1 + r, nb_f[src]));
+    }
+    if (flags & kSqrt) best = __fsqrt_rn(best);
+    const float cur = f[at];
+    if (!(best < fabsf(cur))) break;                          // no outside site helps from here on
+    f[at] = negative ? -best : best;
+  }
+}
+
 }  // namespace edtb200

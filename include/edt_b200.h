@@ -101,6 +101,32 @@ int edtb200_pass_later(const void *labels_dev, int label_bytes, int axis,
                        int border_lo, int border_hi, int flags,
                        float *f_dev, int device, void *stream);
 
+/* Z-slab decomposition across GPUs: a rank runs edtb200_pass_later(axis=2)
+ * on its slab with the interior faces open (border flags 0 there) and then folds the
+ * neighbouring slabs in with these two calls, which replace what the reference gets for free
+ * from having the whole z-line in one address space (src/edt.hpp:465-475).
+ *
+ * edtb200_slab_face_runs : for every (x,y) line, the length m (1..halo) of the run of equal
+ *     labels that touches the low (high_face=0) or high (high_face=1) face of this slab;
+ *     m = halo+1 means "longer than the halo, or spanning the whole slab", and *overflow_dev
+ *     (device int, zeroed by the caller) is raised when that happens for a foreground run
+ *     (any run with EDTB200_SIGNED) -- the caller must then use an exact fallback.
+ * edtb200_slab_face_fixup : after the third-axis pass (same flags: EDTB200_SQRT / SIGNED),
+ *     min-combines every row of the face-touching runs with the neighbour's sites:
+ *     nb_label_dev = the neighbour's face plane of labels, nb_m_dev = its face_runs output,
+ *     nb_f_dev = `halo` planes of the neighbour's distances taken after ITS second-axis pass,
+ *     in the neighbour's z order (its last `halo` planes for our low face, its first for our
+ *     high face).  Requires sz > halo on both sides.
+ */
+int edtb200_slab_face_runs(const void *labels_dev, int label_bytes,
+                           int64_t sx, int64_t sy, int64_t sz, int high_face, int halo, int flags,
+                           unsigned char *m_dev, int *overflow_dev, int device, void *stream);
+
+int edtb200_slab_face_fixup(const void *labels_dev, int label_bytes,
+                            int64_t sx, int64_t sy, int64_t sz, int high_face, int halo, float wz,
+                            int flags, const void *nb_label_dev, const unsigned char *nb_m_dev,
+                            const float *nb_f_dev, float *f_dev, int device, void *stream);
+
 /* Free every cached device buffer / stream this library holds on all devices. */
 int edtb200_release(void);
 

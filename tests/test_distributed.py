@@ -51,6 +51,53 @@ class OraclePasses:
       arr[zero] *= -1.0
 
 
+  # numpy restatement of the two slab-face kernels (edt_kernels.cuh: face_runs_kernel, face_fixup_kernel)
+  def face_runs(self, labels, high_face, halo, signed, overflow):
+    lab = labels.numpy()
+    nz = lab.shape[0]
+    rows = range(nz - 1, -1, -1) if high_face else range(nz)
+    face = lab[nz - 1 if high_face else 0]
+    m = np.zeros(face.shape, dtype=np.int64)
+    alive = np.ones(face.shape, dtype=bool)
+    for k, r in enumerate(rows):
+      if k > halo:
+        break
+      alive &= lab[r] == face
+      m += alive
+    too_long = (m > halo) | (m >= nz)
+    m[too_long] = halo + 1
+    if np.any(too_long & ((face != 0) | bool(signed))):
+      overflow[0] = 1
+    return torch.from_numpy(m.astype(np.uint8))
+
+  def face_fixup(self, labels, f, high_face, halo, wz, sqrt, signed, nb_label, nb_m, nb_f):
+    lab, arr = labels.numpy(), f.numpy()
+    nbl, nbm, nbf = nb_label.numpy(), nb_m.numpy(), nb_f.numpy()
+    nz, sy, sx = lab.shape
+    w2 = np.float32(np.float32(wz) * np.float32(wz))
+    for y in range(sy):
+      for x in range(sx):
+        row0, step = (nz - 1, -1) if high_face else (0, 1)
+        lab0 = lab[row0, y, x]
+        if lab0 == 0 and not signed:
+          continue
+        m = int(nbm[y, x]) if nbl[y, x] == lab0 else 0
+        for j in range(nz):
+          r = row0 + step * j
+          if j > 0 and lab[r, y, x] != lab0:
+            break
+          best = np.float32(np.float64(w2) * (j + 1 + m) ** 2)
+          for k in range(m):
+            src = k if high_face else halo - 1 - k
+            best = min(best, np.float32(np.float64(w2) * (j + 1 + k) ** 2 + np.float64(nbf[src, y, x])))
+          if sqrt:
+            best = np.sqrt(np.float32(best))
+          cur = arr[r, y, x]
+          if not (best < abs(cur)):
+            break
+          arr[r, y, x] = -best if (signed and lab0 == 0) else best
+
+
 def _free_port():
   with socket.socket() as s:
     s.bind(("127.0.0.1", 0))
@@ -65,6 +112,11 @@ def _volume(case):
   elif kind == "ones":
     vol = np.ones(shape, dtype=np.int64)
     vol[tuple(s // 2 for s in shape)] = 0
+  elif kind == "stripes":       # z-runs of length 2 starting at odd z (slab faces cut them), some background
+    z, y, x = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    vol = 1 + ((z + 1) // 2 + x + 2 * y) % 3
+    vol[(x + y) % 4 == 0] = 0
+    vol[:, 1, 1] = np.where(np.arange(shape[0]) % 3 == 0, 0, 5)
   else:
     small = rng.integers(0, 3, tuple((s + 4) // 5 for s in shape))
     vol = np.repeat(np.repeat(np.repeat(small, 5, 0), 5, 1), 5, 2)[:shape[0], :shape[1], :shape[2]]
@@ -90,8 +142,11 @@ def _worker(rank, world, port, queue):
         parts = list(zip(starts.tolist(), depths))
       z0, zc = parts[rank]
       local = torch.from_numpy(vol[z0:z0 + zc].copy())
-      out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed, passes=OraclePasses())
-      queue.put((idx, rank, z0, out.numpy()))
+      for halo in (2, 64):            # 2: the halo method where it is exact; 64: always the transpose
+        info = {}
+        out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed, passes=OraclePasses(), halo=halo,
+                                info=info)
+        queue.put((idx, halo, info["method"], rank, z0, out.numpy()))
   finally:
     dist.destroy_process_group()
 
@@ -104,6 +159,9 @@ CASES = [
   ((10, 4, 9), "ones", (2.0, 1.0, 1.0), True, True, True, None),
   ((7, 3, 4), "blocks", (1.0, 1.0, 1.0), True, False, False, (7, 0)),     # an empty slab
   ((7, 3, 4), "blocks", (1.0, 1.0, 1.0), False, True, True, (0, 3, 4)),   # an empty first slab
+  ((12, 5, 6), "stripes", (1.0, 1.0, 1.0), False, False, False, None),    # halo method applies
+  ((12, 5, 6), "stripes", (2.0, 3.0, 1.0), True, True, True, None),
+  ((13, 4, 5), "stripes", (0.7, 1.0, 1.3), False, True, False, None),
 ]
 
 
@@ -118,22 +176,31 @@ def test_slab_split_matches_single_volume(world):
   for p in procs:
     p.start()
   active = [i for i, c in enumerate(CASES) if c[6] is None or len(c[6]) == world]
-  results = [queue.get(timeout=300) for _ in range(world * len(active))]
+  results = [queue.get(timeout=300) for _ in range(2 * world * len(active))]
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
   assert len(active) >= 6
+  used = set()
   for idx in active:
     case = CASES[idx]
     shape, kind, an, bb, sqrt, signed, _ = case
-    got = np.zeros(shape, dtype=np.float32)
-    for i, rank, z0, arr in results:
-      if i == idx:
-        got[z0:z0 + arr.shape[0]] = arr
     fn = {(False, False): oracle.edtsq, (True, False): oracle.edt,
           (False, True): oracle.sdfsq, (True, True): oracle.sdf}[(sqrt, signed)]
     want = fn(_volume(case), anisotropy=an, black_border=bb)    # the same volume, not distributed
-    assert np.array_equal(got, want, equal_nan=True), (world, idx)
+    for halo in (2, 64):
+      got = np.zeros(shape, dtype=np.float32)
+      methods = set()
+      for i, h, method, rank, z0, arr in results:
+        if i == idx and h == halo:
+          got[z0:z0 + arr.shape[0]] = arr
+          methods.add(method)
+      assert len(methods) == 1, (world, idx, halo, methods)       # every rank took the same path
+      if halo == 64:
+        assert methods == {"transpose"}
+      used.add((idx, methods.pop()))
+      assert np.array_equal(got, want, equal_nan=True), (world, idx, halo)
+  assert any(m == "halo" for _, m in used) and any(m == "transpose" for _, m in used), used
 
 
 def test_split_extent():
@@ -165,10 +232,13 @@ def _nccl_worker(rank, world, port, queue):
       parts = ed.split_extent(vol.shape[0], world)
       z0, zc = parts[rank]
       local = torch.from_numpy(vol[z0:z0 + zc].copy()).cuda()
-      out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed)
       whole = edt_b200.edt_cuda(torch.from_numpy(vol).cuda(), an, bb, sqrt=sqrt, signed=signed)
-      torch.cuda.synchronize()
-      queue.put((rank, bool(torch.equal(out, whole[z0:z0 + zc]))))
+      for method in ("auto", "transpose"):
+        info = {}
+        out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed, method=method, info=info)
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(out, whole[z0:z0 + zc])) and info["method"] == ("halo" if method == "auto" else "transpose")
+        queue.put((rank, ok))
   finally:
     dist.destroy_process_group()
 
@@ -183,7 +253,7 @@ def test_slab_split_nccl_two_gpus():
   procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, queue)) for r in range(2)]
   for p in procs:
     p.start()
-  results = [queue.get(timeout=300) for _ in range(4)]
+  results = [queue.get(timeout=300) for _ in range(8)]
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
