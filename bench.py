@@ -27,6 +27,9 @@ import time
 
 import numpy as np
 
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+  os.environ["NCCL_DEBUG"] = "WARN"              # keep NCCL's version banner off stdout (one JSON line only)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)

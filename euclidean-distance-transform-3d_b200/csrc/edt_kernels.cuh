@@ -1034,7 +1034,8 @@ face_fixup_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, floa
   const bool background = lab0 == 0;
   if (background && !(flags & kZeroLabel)) return;            // plain EDT: background stays 0
   const bool same = nb_label[q] == lab0;
-  const int m = same ? (int)nb_m[q] : 0;                      // neighbour rows of this run (<= H)
+  const int m = same ? min((int)nb_m[q], H) : 0;              // neighbour rows of this run (<= H; H + 1 means
+                                                              // "too long": the caller discards this result)
   const bool negative = (flags & kNegate) && background;
   for (int j = 0; j < nz; ++j) {
     const int64_t at = (row0 + step * j) * plane + q;

@@ -138,6 +138,14 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   rank = dist.get_rank(group)
   if passes is None:
     passes = CudaPasses(labels_local.device)
+  marks = info.get("marks") if isinstance(info, dict) else None      # optional CUDA-event phase marks
+
+  def mark(name):
+    if marks is not None:
+      ev = torch.cuda.Event(enable_timing=True)
+      ev.record()
+      marks.append((name, ev))
+  mark("start")
   if labels_local.dim() != 3:
     raise TypeError("slab_transform expects a 3-D (z, y, x) slab")
   labels_local = labels_local.contiguous()
@@ -161,6 +169,7 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     if rank < world - 1:
       m_hi = passes.face_runs(labels_local, 1, halo, signed, overflow)
     dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=group)
+  mark("face_runs+allreduce")
 
   # ---- X and Y passes: slab-local, no communication ----
   f = passes.empty_f32((zc, sy, sx))
@@ -168,6 +177,7 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   if zc:
     passes.pass_first(labels_local, f, wx, black_border, signed)
     passes.pass_later(labels_local, f, 1, wy, black_border, black_border)
+  mark("x+y passes")
   if single:
     if zc:
       passes.pass_later(labels_local, f, 2, wz, black_border, black_border, sqrt=sqrt, negate=signed)
@@ -175,11 +185,8 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
       info["method"] = "single"
     return f
 
-  if use_halo and int(overflow.item()) != 0:       # (the X and Y kernels are already queued)
-    use_halo = False
   if method == "halo" and not use_halo:
-    raise EDTError("halo method is not exact here: a run reaches deeper than %d rows into a neighbouring "
-                   "slab (or a slab is not deeper than the halo)" % halo)
+    raise EDTError("halo method needs more than one rank and slabs deeper than the halo (%d)" % halo)
   if info is not None:
     info["method"] = "halo" if use_halo else "transpose"
 
@@ -205,15 +212,27 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
       for t in (r_label, r_m, r_f):
         ops.append(dist.P2POp(dist.irecv, t, peer, group))
     reqs = dist.batch_isend_irecv(ops) if ops else []
+    mark("halo clone + exchange posted")
     # ---- Z pass on the slab, interior faces open; overlaps with the exchange ----
     passes.pass_later(labels_local, f, 2, wz, black_border and rank == 0, black_border and rank == world - 1,
                       sqrt=sqrt, negate=signed)
+    mark("z pass")
     for req in reqs:
       req.wait()
+    mark("exchange done")
     for high_face, (r_label, r_m, r_f) in recv.items():
       nb_label = r_label.view(labels_local.dtype).reshape(sy, sx)
       passes.face_fixup(labels_local, f, high_face, halo, wz, sqrt, signed, nb_label, r_m, r_f)
-    return f
+    mark("face fix-up")
+    # The halo path was taken optimistically so that the host never waits in the middle of a
+    # step; only now, with everything queued, is the (all-reduced) verdict of face_runs read.
+    if int(overflow.item()) == 0:
+      return f
+    if method == "halo":
+      raise EDTError("halo method is not exact here: a run reaches deeper than %d rows into a "
+                     "neighbouring slab" % halo)
+    return slab_transform(labels_local, anisotropy, black_border, sqrt=sqrt, signed=signed, group=group,
+                          passes=passes, halo=halo, method="transpose", info=info)
 
   # ---- Z pass: Z slabs -> Y slabs (all-to-all), pass, back ----
   ysplit = split_extent(sy, world)
