@@ -21,6 +21,11 @@ split along the slowest axis into contiguous slabs, one per rank.
     back.  Per GPU and step it moves (4 + L) * N/G * (G-1)/G bytes forward and 4 * N/G * (G-1)/G
     back over NVLink (L = label bytes, N = voxels, G = ranks).
 
+For the exchange to overlap with the Z-pass kernel (which fills every SM), create the process
+group with a high-priority NCCL stream:
+    opts = torch.distributed.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    torch.distributed.init_process_group("nccl", pg_options=opts, ...)
+
 All collectives are grouped point-to-point operations (`batch_isend_irecv`), which NCCL executes as
 one fused all-to-all over NVSwitch and which gloo also implements, so the same code path is
 exercised by the CPU tests (world_size 2, gloo) with the oracle standing in for the kernels.
@@ -124,7 +129,7 @@ def _peer(group, r):
 
 
 def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False, *, sqrt=False,
-                   signed=False, group=None, passes=None, halo=32, method="auto", info=None):
+                   signed=False, group=None, passes=None, halo=32, method="auto", info=None, depths=None):
   """Distance transform of a volume distributed as Z slabs (axis 0) over the ranks of `group`.
 
   labels_local : this rank's slab, integer tensor (zc, sy, sx), C-contiguous; slabs are ordered by
@@ -133,6 +138,7 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   edt (sqrt=True), sdfsq (signed=True) and sdf (both) of the reference, on the WHOLE volume.
   method: "auto" (halo exchange when it is exact for these labels, else transpose), "halo"
   (raise if not exact), "transpose".  `info`, if a dict, receives {"method": ...}.
+  depths: slab depth of every rank, if the caller knows them (saves one small all-reduce per call).
   """
   world = dist.get_world_size(group)
   rank = dist.get_rank(group)
@@ -153,10 +159,15 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   zc, sy, sx = labels_local.shape
 
   # slab depths of every rank (needed for the exchange geometry)
-  depths = torch.zeros(world, dtype=torch.int64, device=labels_local.device)
-  depths[rank] = zc
-  dist.all_reduce(depths, group=group)
-  depths = [int(d) for d in depths.tolist()]
+  if depths is None:
+    dt = torch.zeros(world, dtype=torch.int64, device=labels_local.device)
+    dt[rank] = zc
+    dist.all_reduce(dt, group=group)
+    depths = [int(d) for d in dt.tolist()]
+  else:
+    depths = [int(d) for d in depths]
+    if len(depths) != world or depths[rank] != zc:
+      raise ValueError("depths must list the slab depth of every rank")
   sz = sum(depths)
 
   # ---- can the halo method be used?  decided on the labels alone, before any pass runs ----
@@ -168,7 +179,8 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
       m_lo = passes.face_runs(labels_local, 0, halo, signed, overflow)
     if rank < world - 1:
       m_hi = passes.face_runs(labels_local, 1, halo, signed, overflow)
-    dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=group)
+    # asynchronous: the compute stream must not wait for this tiny collective
+    overflow_work = dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=group, async_op=True)
   mark("face_runs+allreduce")
 
   # ---- X and Y passes: slab-local, no communication ----
@@ -226,13 +238,14 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     mark("face fix-up")
     # The halo path was taken optimistically so that the host never waits in the middle of a
     # step; only now, with everything queued, is the (all-reduced) verdict of face_runs read.
+    overflow_work.wait()
     if int(overflow.item()) == 0:
       return f
     if method == "halo":
       raise EDTError("halo method is not exact here: a run reaches deeper than %d rows into a "
                      "neighbouring slab" % halo)
     return slab_transform(labels_local, anisotropy, black_border, sqrt=sqrt, signed=signed, group=group,
-                          passes=passes, halo=halo, method="transpose", info=info)
+                          passes=passes, halo=halo, method="transpose", info=info, depths=depths)
 
   # ---- Z pass: Z slabs -> Y slabs (all-to-all), pass, back ----
   ysplit = split_extent(sy, world)
