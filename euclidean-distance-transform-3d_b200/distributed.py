@@ -85,11 +85,11 @@ class CudaPasses:
                                             f.data_ptr(), self.device.index, self._stream()))
 
 
-  def face_runs(self, labels, high_face, halo, signed, overflow):
+  def face_runs(self, labels, high_face, halo, signed, overflow, out=None):
     """uint8 (sy, sx) run lengths at one face; raises the device int `overflow` when too long."""
     sz, sy, sx = labels.shape
     nbytes = _torch_label_bytes(torch)[labels.dtype]
-    m = torch.empty((sy, sx), dtype=torch.uint8, device=self.device)
+    m = out if out is not None else torch.empty((sy, sx), dtype=torch.uint8, device=self.device)
     self._check(self.lib.edtb200_slab_face_runs(labels.data_ptr(), nbytes, sx, sy, sz, int(high_face), int(halo),
                                                 FLAG_SIGNED if signed else 0, m.data_ptr(),
                                                 overflow.data_ptr(), self.device.index, self._stream()))
@@ -124,12 +124,78 @@ def _all_to_all(send_chunks, recv_chunks, group):
       req.wait()
 
 
+class PeerHalo:
+  """Face staging buffers in CUDA symmetric memory (torch.distributed._symmetric_memory): every
+  rank publishes, per step, its two face planes of labels, its face run lengths and its first /
+  last `halo` planes of Y-pass distances in a buffer that its neighbours map over NVLink, and
+  the neighbours' `face_fixup_kernel` READS them in place -- only the rows it actually needs
+  (typically one or two planes), instead of receiving all `halo` planes through NCCL.
+  Two parity sets + pairwise put_signal / wait_signal order writers and readers across steps:
+  a rank overwrites set p at step k+2 only after it has seen its neighbours' step-(k+1) signal,
+  which they issue after their step-k fix-up (the last reader of set p).
+
+  Creating one is a collective call over `group`; reuse it for every transform of the same
+  (sy, sx, label dtype, halo)."""
+
+  def __init__(self, device, sy, sx, label_dtype, halo=32, group=None):
+    import torch.distributed._symmetric_memory as symm_mem
+    self.group = group if group is not None else dist.group.WORLD
+    self.rank = dist.get_rank(group)
+    self.world = dist.get_world_size(group)
+    self.halo, self.sy, self.sx = int(halo), int(sy), int(sx)
+    self.dtype = label_dtype
+    esz = torch.empty((), dtype=label_dtype).element_size()
+    plane = self.sy * self.sx
+    pad = lambda n: (n + 255) // 256 * 256
+    self.layout, off = {}, 0
+    for name, nbytes in (("f_lo", self.halo * plane * 4), ("f_hi", self.halo * plane * 4),
+                         ("lab_lo", plane * esz), ("lab_hi", plane * esz), ("m_lo", plane), ("m_hi", plane)):
+      self.layout[name] = (off, nbytes)
+      off += pad(nbytes)
+    self.set_bytes = off
+    self.buf = symm_mem.empty(2 * self.set_bytes, dtype=torch.uint8, device=device)
+    self.hdl = symm_mem.rendezvous(self.buf, self.group)
+    self.step = 0
+    self._flat = {}
+
+  def matches(self, sy, sx, label_dtype, halo):
+    return (self.sy, self.sx, self.dtype, self.halo) == (int(sy), int(sx), label_dtype, int(halo))
+
+  def views(self, rank, parity):
+    """Typed views of `rank`'s staging set `parity` (own memory or a peer's, mapped over NVLink)."""
+    if rank not in self._flat:
+      self._flat[rank] = self.buf if rank == self.rank else \
+          self.hdl.get_buffer(rank, (2 * self.set_bytes,), torch.uint8, 0)
+    flat = self._flat[rank]
+    base = parity * self.set_bytes
+    out = {}
+    for name, (off, nbytes) in self.layout.items():
+      raw = flat[base + off: base + off + nbytes]
+      if name.startswith("f_"):
+        out[name] = raw.view(torch.float32).reshape(self.halo, self.sy, self.sx)
+      elif name.startswith("lab_"):
+        out[name] = raw.view(self.dtype).reshape(self.sy, self.sx)
+      else:
+        out[name] = raw.reshape(self.sy, self.sx)
+    return out
+
+
+def make_peer_halo(device, sy, sx, label_dtype, halo=32, group=None):
+  """PeerHalo, or (None, reason) when symmetric memory is unavailable (then slab_transform uses
+  the NCCL send/recv exchange).  Collective over `group`; returns (peer_halo, reason)."""
+  try:
+    return PeerHalo(device, sy, sx, label_dtype, halo, group), None
+  except Exception as exc:            # e.g. no P2P access between the GPUs, or an older torch
+    return None, "%s: %s" % (type(exc).__name__, exc)
+
+
 def _peer(group, r):
   return dist.get_global_rank(group, r) if group is not None else r
 
 
 def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False, *, sqrt=False,
-                   signed=False, group=None, passes=None, halo=32, method="auto", info=None, depths=None):
+                   signed=False, group=None, passes=None, halo=32, method="auto", info=None, depths=None,
+                   peer_halo=None):
   """Distance transform of a volume distributed as Z slabs (axis 0) over the ranks of `group`.
 
   labels_local : this rank's slab, integer tensor (zc, sy, sx), C-contiguous; slabs are ordered by
@@ -139,6 +205,8 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   method: "auto" (halo exchange when it is exact for these labels, else transpose), "halo"
   (raise if not exact), "transpose".  `info`, if a dict, receives {"method": ...}.
   depths: slab depth of every rank, if the caller knows them (saves one small all-reduce per call).
+  peer_halo: a PeerHalo (symmetric-memory staging); the fix-up then reads the neighbours' faces
+  directly over NVLink instead of receiving `halo` planes through NCCL send/recv.
   """
   world = dist.get_world_size(group)
   rank = dist.get_rank(group)
@@ -175,10 +243,17 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   m_lo = m_hi = None
   if use_halo:
     overflow = torch.zeros(1, dtype=torch.int32, device=labels_local.device)
+    stage = None
+    if peer_halo is not None:
+      if not peer_halo.matches(sy, sx, labels_local.dtype, halo):
+        raise ValueError("peer_halo was created for another plane shape / dtype / halo")
+      parity = peer_halo.step & 1
+      peer_halo.step += 1
+      stage = peer_halo.views(rank, parity)
     if rank > 0:
-      m_lo = passes.face_runs(labels_local, 0, halo, signed, overflow)
+      m_lo = passes.face_runs(labels_local, 0, halo, signed, overflow, out=stage["m_lo"] if stage else None)
     if rank < world - 1:
-      m_hi = passes.face_runs(labels_local, 1, halo, signed, overflow)
+      m_hi = passes.face_runs(labels_local, 1, halo, signed, overflow, out=stage["m_hi"] if stage else None)
     # asynchronous: the compute stream must not wait for this tiny collective
     overflow_work = dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=group, async_op=True)
   mark("face_runs+allreduce")
@@ -201,6 +276,38 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     raise EDTError("halo method needs more than one rank and slabs deeper than the halo (%d)" % halo)
   if info is not None:
     info["method"] = "halo" if use_halo else "transpose"
+
+  if use_halo and peer_halo is not None:
+    # ---- publish my faces in symmetric memory, signal the neighbours, Z pass, read theirs ----
+    stage["f_lo"].copy_(f[:halo])
+    stage["f_hi"].copy_(f[zc - halo:])
+    stage["lab_lo"].copy_(labels_local[0])
+    stage["lab_hi"].copy_(labels_local[zc - 1])
+    nbs = [nb for nb in (rank - 1, rank + 1) if 0 <= nb < world]
+    for nb in nbs:
+      peer_halo.hdl.put_signal(nb, parity)
+    mark("faces staged + signalled")
+    passes.pass_later(labels_local, f, 2, wz, black_border and rank == 0, black_border and rank == world - 1,
+                      sqrt=sqrt, negate=signed)
+    mark("z pass")
+    for nb in nbs:
+      peer_halo.hdl.wait_signal(nb, parity)
+    mark("neighbours ready")
+    if rank > 0:
+      nbv = peer_halo.views(rank - 1, parity)
+      passes.face_fixup(labels_local, f, 0, halo, wz, sqrt, signed, nbv["lab_hi"], nbv["m_hi"], nbv["f_hi"])
+    if rank < world - 1:
+      nbv = peer_halo.views(rank + 1, parity)
+      passes.face_fixup(labels_local, f, 1, halo, wz, sqrt, signed, nbv["lab_lo"], nbv["m_lo"], nbv["f_lo"])
+    mark("face fix-up (peer reads)")
+    overflow_work.wait()
+    if int(overflow.item()) == 0:
+      return f
+    if method == "halo":
+      raise EDTError("halo method is not exact here: a run reaches deeper than %d rows into a "
+                     "neighbouring slab" % halo)
+    return slab_transform(labels_local, anisotropy, black_border, sqrt=sqrt, signed=signed, group=group,
+                          passes=passes, halo=halo, method="transpose", info=info, depths=depths)
 
   if use_halo:
     # ---- one neighbour exchange: face labels, face run lengths, `halo` planes of distances ----

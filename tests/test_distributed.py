@@ -52,7 +52,7 @@ class OraclePasses:
 
 
   # numpy restatement of the two slab-face kernels (edt_kernels.cuh: face_runs_kernel, face_fixup_kernel)
-  def face_runs(self, labels, high_face, halo, signed, overflow):
+  def face_runs(self, labels, high_face, halo, signed, overflow, out=None):
     lab = labels.numpy()
     nz = lab.shape[0]
     rows = range(nz - 1, -1, -1) if high_face else range(nz)
@@ -129,6 +129,17 @@ def _worker(rank, world, port, queue):
   os.environ["MASTER_PORT"] = str(port)
   dist.init_process_group("gloo", rank=rank, world_size=world)
   try:
+    _worker_body(rank, world, queue)
+  except Exception as exc:          # surface the failure instead of letting the peers time out
+    import traceback
+    queue.put(("error", rank, traceback.format_exc()))
+    raise
+  finally:
+    dist.destroy_process_group()
+
+
+def _worker_body(rank, world, queue):
+  if True:
     import edt_b200.distributed as ed
     for idx, case in enumerate(CASES):
       shape, kind, an, bb, sqrt, signed, depths = case
@@ -147,8 +158,6 @@ def _worker(rank, world, port, queue):
         out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed, passes=OraclePasses(), halo=halo,
                                 info=info)
         queue.put((idx, halo, info["method"], rank, z0, out.numpy()))
-  finally:
-    dist.destroy_process_group()
 
 
 CASES = [
@@ -176,7 +185,11 @@ def test_slab_split_matches_single_volume(world):
   for p in procs:
     p.start()
   active = [i for i, c in enumerate(CASES) if c[6] is None or len(c[6]) == world]
-  results = [queue.get(timeout=300) for _ in range(2 * world * len(active))]
+  results = []
+  for _ in range(2 * world * len(active)):
+    item = queue.get(timeout=300)
+    assert item[0] != "error", item
+    results.append(item)
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
@@ -225,6 +238,7 @@ def _nccl_worker(rank, world, port, queue):
     import edt_b200
     import edt_b200.distributed as ed
     rng = np.random.default_rng(99)
+    peer_halo, peer_why = ed.make_peer_halo(torch.device("cuda", rank), 54, 70, torch.int32, 32)
     # (a) z-runs of exactly 4 planes plus an iid region: the halo method is exact here
     z, y, x = np.meshgrid(np.arange(143), np.arange(54), np.arange(70), indexing="ij")
     vol_a = (1 + ((z // 4) + (y // 9) * 3 + (x // 10) * 7) % 5).astype(np.int32)
@@ -238,13 +252,17 @@ def _nccl_worker(rank, world, port, queue):
         z0, zc = parts[rank]
         local = torch.from_numpy(vol[z0:z0 + zc].copy()).cuda()
         whole = edt_b200.edt_cuda(torch.from_numpy(vol).cuda(), an, bb, sqrt=sqrt, signed=signed)
-        for method in ("auto", "transpose"):
+        for method, peer in (("auto", None), ("transpose", None), ("auto", peer_halo)):
+          if method == "auto" and peer is None and peer_halo is not None and False:
+            continue
           info = {}
-          out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed, method=method, info=info)
+          out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed, method=method, info=info,
+                                  peer_halo=peer)
           torch.cuda.synchronize()
           want_method = expect if method == "auto" else "transpose"
           bad = int((out != whole[z0:z0 + zc]).sum().item())
-          queue.put((rank, bad == 0 and info["method"] == want_method, bad, info["method"], want_method))
+          queue.put((rank, bad == 0 and info["method"] == want_method, bad, info["method"], want_method,
+                     "peer" if peer is not None else "nccl", peer_why))
   finally:
     dist.destroy_process_group()
 
@@ -259,7 +277,7 @@ def test_slab_split_nccl_two_gpus():
   procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, queue)) for r in range(2)]
   for p in procs:
     p.start()
-  results = [queue.get(timeout=300) for _ in range(16)]
+  results = [queue.get(timeout=300) for _ in range(24)]
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0

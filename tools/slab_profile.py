@@ -15,15 +15,18 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local),
 g = torch.Generator(device="cuda"); g.manual_seed(rank)
 lab = torch.randint(0, 256, (512, 512, 512), dtype=torch.int32, device="cuda", generator=g)
 passes = ed.CudaPasses(torch.device("cuda", local))
+peer, why = ed.make_peer_halo(torch.device("cuda", local), 512, 512, torch.int32, 32)
+if rank == 0: print("peer halo:", "ok" if peer is not None else why)
+if os.environ.get("NO_PEER"): peer = None
 for _ in range(3):
-  ed.slab_transform(lab, passes=passes)
+  ed.slab_transform(lab, passes=passes, peer_halo=peer)
 torch.cuda.synchronize(); dist.barrier()
 acc = {}
 wall = []
 for it in range(10):
   info = {"marks": []}
   t0 = time.perf_counter()
-  ed.slab_transform(lab, passes=passes, info=info, depths=[512] * world)
+  ed.slab_transform(lab, passes=passes, info=info, depths=[512] * world, peer_halo=peer)
   t1 = time.perf_counter()
   torch.cuda.synchronize()
   wall.append((t1 - t0) * 1e3)
