@@ -143,8 +143,8 @@ class PeerHalo:
     self.rank = dist.get_rank(group)
     self.world = dist.get_world_size(group)
     self.halo, self.sy, self.sx = int(halo), int(sy), int(sx)
-    self.dtype = label_dtype
     esz = torch.empty((), dtype=label_dtype).element_size()
+    self.esz = esz
     plane = self.sy * self.sx
     pad = lambda n: (n + 255) // 256 * 256
     self.layout, off = {}, 0
@@ -159,7 +159,8 @@ class PeerHalo:
     self._flat = {}
 
   def matches(self, sy, sx, label_dtype, halo):
-    return (self.sy, self.sx, self.dtype, self.halo) == (int(sy), int(sx), label_dtype, int(halo))
+    esz = torch.empty((), dtype=label_dtype).element_size()
+    return (self.sy, self.sx, self.esz, self.halo) == (int(sy), int(sx), esz, int(halo))
 
   def views(self, rank, parity):
     """Typed views of `rank`'s staging set `parity` (own memory or a peer's, mapped over NVLink)."""
@@ -174,7 +175,7 @@ class PeerHalo:
       if name.startswith("f_"):
         out[name] = raw.view(torch.float32).reshape(self.halo, self.sy, self.sx)
       elif name.startswith("lab_"):
-        out[name] = raw.view(self.dtype).reshape(self.sy, self.sx)
+        out[name] = raw.reshape(self.sy, self.sx * self.esz)        # raw label bytes
       else:
         out[name] = raw.reshape(self.sy, self.sx)
     return out
@@ -281,8 +282,9 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     # ---- publish my faces in symmetric memory, signal the neighbours, Z pass, read theirs ----
     stage["f_lo"].copy_(f[:halo])
     stage["f_hi"].copy_(f[zc - halo:])
-    stage["lab_lo"].copy_(labels_local[0])
-    stage["lab_hi"].copy_(labels_local[zc - 1])
+    lab_bytes = labels_local.view(torch.uint8).reshape(zc, sy, sx * labels_local.element_size())
+    stage["lab_lo"].copy_(lab_bytes[0])
+    stage["lab_hi"].copy_(lab_bytes[zc - 1])
     nbs = [nb for nb in (rank - 1, rank + 1) if 0 <= nb < world]
     for nb in nbs:
       peer_halo.hdl.put_signal(nb, parity)
@@ -295,10 +297,12 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     mark("neighbours ready")
     if rank > 0:
       nbv = peer_halo.views(rank - 1, parity)
-      passes.face_fixup(labels_local, f, 0, halo, wz, sqrt, signed, nbv["lab_hi"], nbv["m_hi"], nbv["f_hi"])
+      passes.face_fixup(labels_local, f, 0, halo, wz, sqrt, signed, nbv["lab_hi"].view(labels_local.dtype),
+                        nbv["m_hi"], nbv["f_hi"])
     if rank < world - 1:
       nbv = peer_halo.views(rank + 1, parity)
-      passes.face_fixup(labels_local, f, 1, halo, wz, sqrt, signed, nbv["lab_lo"], nbv["m_lo"], nbv["f_lo"])
+      passes.face_fixup(labels_local, f, 1, halo, wz, sqrt, signed, nbv["lab_lo"].view(labels_local.dtype),
+                        nbv["m_lo"], nbv["f_lo"])
     mark("face fix-up (peer reads)")
     overflow_work.wait()
     if int(overflow.item()) == 0:
