@@ -157,6 +157,7 @@ class PeerHalo:
     self.hdl = symm_mem.rendezvous(self.buf, self.group)
     self.step = 0
     self._flat = {}
+    self._views = {}
 
   def matches(self, sy, sx, label_dtype, halo):
     esz = torch.empty((), dtype=label_dtype).element_size()
@@ -164,6 +165,8 @@ class PeerHalo:
 
   def views(self, rank, parity):
     """Typed views of `rank`'s staging set `parity` (own memory or a peer's, mapped over NVLink)."""
+    if (rank, parity) in self._views:
+      return self._views[(rank, parity)]
     if rank not in self._flat:
       self._flat[rank] = self.buf if rank == self.rank else \
           self.hdl.get_buffer(rank, (2 * self.set_bytes,), torch.uint8, 0)
@@ -178,7 +181,17 @@ class PeerHalo:
         out[name] = raw.reshape(self.sy, self.sx * self.esz)        # raw label bytes
       else:
         out[name] = raw.reshape(self.sy, self.sx)
+    self._views[(rank, parity)] = out
     return out
+
+
+def check_verdicts(verdicts):
+  """True if every deferred halo verdict (info["verdict"] of slab_transform) is clean."""
+  worst = 0
+  for flag, work in verdicts:
+    work.wait()
+    worst = max(worst, int(flag.item()))
+  return worst == 0
 
 
 def make_peer_halo(device, sy, sx, label_dtype, halo=32, group=None):
@@ -196,7 +209,7 @@ def _peer(group, r):
 
 def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False, *, sqrt=False,
                    signed=False, group=None, passes=None, halo=32, method="auto", info=None, depths=None,
-                   peer_halo=None):
+                   peer_halo=None, defer_check=False):
   """Distance transform of a volume distributed as Z slabs (axis 0) over the ranks of `group`.
 
   labels_local : this rank's slab, integer tensor (zc, sy, sx), C-contiguous; slabs are ordered by
@@ -208,6 +221,11 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   depths: slab depth of every rank, if the caller knows them (saves one small all-reduce per call).
   peer_halo: a PeerHalo (symmetric-memory staging); the fix-up then reads the neighbours' faces
   directly over NVLink instead of receiving `halo` planes through NCCL send/recv.
+  defer_check: the halo method is taken optimistically and its exactness verdict (a device int,
+  all-reduced) is normally read at the end of the call, which costs one host synchronisation.
+  With defer_check=True the call returns without reading it and puts it in info["verdict"]
+  (call `check_verdicts` on a batch of them later); a non-zero verdict means the result must be
+  recomputed with method="transpose".
   """
   world = dist.get_world_size(group)
   rank = dist.get_rank(group)
@@ -304,6 +322,11 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
       passes.face_fixup(labels_local, f, 1, halo, wz, sqrt, signed, nbv["lab_lo"].view(labels_local.dtype),
                         nbv["m_lo"], nbv["f_lo"])
     mark("face fix-up (peer reads)")
+    if defer_check:
+      if info is None:
+        raise ValueError("defer_check=True needs an `info` dict to receive the verdict")
+      info["verdict"] = (overflow, overflow_work)
+      return f
     overflow_work.wait()
     if int(overflow.item()) == 0:
       return f
@@ -349,6 +372,11 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     mark("face fix-up")
     # The halo path was taken optimistically so that the host never waits in the middle of a
     # step; only now, with everything queued, is the (all-reduced) verdict of face_runs read.
+    if defer_check:
+      if info is None:
+        raise ValueError("defer_check=True needs an `info` dict to receive the verdict")
+      info["verdict"] = (overflow, overflow_work)
+      return f
     overflow_work.wait()
     if int(overflow.item()) == 0:
       return f

@@ -26,7 +26,7 @@ wall = []
 for it in range(10):
   info = {"marks": []}
   t0 = time.perf_counter()
-  ed.slab_transform(lab, passes=passes, info=info, depths=[512] * world, peer_halo=peer)
+  ed.slab_transform(lab, passes=passes, info=info, depths=[512] * world, peer_halo=peer, defer_check=True)
   t1 = time.perf_counter()
   torch.cuda.synchronize()
   wall.append((t1 - t0) * 1e3)
