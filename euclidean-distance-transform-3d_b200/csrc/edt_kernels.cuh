@@ -608,6 +608,22 @@ __device__ __forceinline__ void read_out_local(const TileLine<TX> ln, uint32_t h
   }
 }
 
+// True if every sample of rows [sa, sb) equals the first one (returned in f0).  Equal-height
+// parabolas never hide one another, so a constant segment needs no envelope scan at all: every
+// row is its own best site and its value is min(f0, border terms).  This is the common case
+// inside blocky segmentations and inside large binary objects along the later axes.
+template <int TX>
+__device__ __forceinline__ bool segment_constant(const TileLine<TX> ln, int sa, int sb, float& f0) {
+  uint32_t at = ln.f + (uint32_t)sa * TileLine<TX>::ROW;
+  f0 = lds_f32(at);
+  bool same = true;
+  for (int r = sa + 1; r < sb; ++r) {
+    at += TileLine<TX>::ROW;
+    same = same && (lds_f32(at) == f0);
+  }
+  return same;
+}
+
 // Lower envelope of the finite samples of rows [sa, sb) (sb - o <= 32), as a bit mask relative
 // to row `o`: returns hb with the bits of the surviving vertices set (other bits untouched).
 // Classic stack scan with the stack kept as bits: top vertex q, the one below it p, and
@@ -810,12 +826,32 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           }
           sb = next_start;
         }
+        float f0;
         if (sb - sa <= 32) {
-          const uint32_t lb = build_hull<TX>(ln, sa, sa, sb, w2d, 0u);
-          read_out_local<TX, Epilogue>(ln, lb, sa, sa, sb, w2, sa > 0 || border_lo, sb < n || border_hi, sq_t,
-                                       line0, pitch, (wzero >> r0) & 1u, flags);
+          const bool lo_b = sa > 0 || border_lo, hi_b = sb < n || border_hi;
+          if (segment_constant<TX>(ln, sa, sb, f0)) {
+            char* dst = line0 + (size_t)sa * pitch;
+            uint32_t sq_lo = sq_t + 4u, sq_hi = sq_t + (uint32_t)(sb - sa) * 4u;
+            for (int i = sa; i < sb; ++i) {
+              float best = f0;
+              if (lo_b) best = fminf(best, lds_f32(sq_lo));
+              if (hi_b) best = fminf(best, lds_f32(sq_hi));
+              sq_lo += 4u; sq_hi -= 4u;
+              if (Epilogue) best = finish_value(best, (wzero >> r0) & 1u, flags);
+              *reinterpret_cast<float*>(dst) = best;
+              dst += pitch;
+            }
+          } else {
+            const uint32_t lb = build_hull<TX>(ln, sa, sa, sb, w2d, 0u);
+            read_out_local<TX, Epilogue>(ln, lb, sa, sa, sb, w2, lo_b, hi_b, sq_t, line0, pitch,
+                                         (wzero >> r0) & 1u, flags);
+          }
         } else {
-          hb = build_hull<TX>(ln, i0, sa, i0 + 32, w2d, hb);
+          if (segment_constant<TX>(ln, sa, i0 + 32, f0)) {
+            if (f0 < inf) hb |= 0xffffffffu << r0;            // every row is a vertex
+          } else {
+            hb = build_hull<TX>(ln, i0, sa, i0 + 32, w2d, hb);
+          }
           crossing = 1;
         }
       }
@@ -840,7 +876,13 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           b_run = next_start;
         } else b_run = min(n, i0 + 32);
         if (b_run - a_lo > 32) {
-          hb = build_hull<TX>(ln, i0, i0, min(b_run, i0 + rows), w2d, hb);
+          const int seg_end = min(b_run, i0 + rows);
+          float f0;
+          if (segment_constant<TX>(ln, i0, seg_end, f0)) {
+            if (f0 < inf) hb |= (seg_end - i0 == 32) ? 0xffffffffu : ((1u << (seg_end - i0)) - 1u);
+          } else {
+            hb = build_hull<TX>(ln, i0, i0, seg_end, w2d, hb);
+          }
           crossing = 1;
         }
       }
@@ -850,35 +892,63 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   if (!__syncthreads_or(crossing)) return;                 // every run was finished inside its chunk
 
   // ============ stage 2: stitch the hulls of runs that cross chunk boundaries ============
-  // One thread per line walks the boundaries bottom-up.  Left of a boundary stands the final
-  // hull of everything below (A), right of it the local hull of the next chunk's first segment
-  // (B); all of A lies left of all of B, so their union's hull is a prefix of A plus a suffix of
-  // B: drop A's top while it is hidden by (the vertex below it, B's first), drop B's first while
-  // it is hidden by (A's top, B's second), until neither applies.
-  if (live && threadIdx.x < TX) {
-    int a = 0;                                             // start of the run open at the boundary
-    for (int c = 1; c < nchunks; ++c) {
-      const int i0 = c << 5;
-      const uint32_t wprev = lds_u32(startcol + (uint32_t)(c - 1) * ROW);
-      if (wprev) a = ((c - 1) << 5) + 31 - __clz(wprev);
-      const uint32_t wc = lds_u32(startcol + (uint32_t)c * ROW);
-      if (wc & 1u) continue;                               // a run starts exactly here: nothing crosses
-      const int sb = wc ? (i0 + __ffs(wc) - 1) : min(n, i0 + 32);
-      for (;;) {
-        const int av = prev_vertex<TX>(ln, i0, a);
-        if (av < 0) break;
-        const int bv = next_vertex<TX>(ln, i0 - 1, sb);
-        if (bv < 0) break;
-        const float fa = ln.fval(av), fb = ln.fval(bv);
-        const int ap = prev_vertex<TX>(ln, av, a);
-        if (ap >= 0 && vertex_hidden(ap, ln.fval(ap), av, fa, bv, fb, w2d)) { ln.drop(av); continue; }
-        const int bn = next_vertex<TX>(ln, bv, sb);
-        if (bn >= 0 && vertex_hidden(av, fa, bv, fb, bn, ln.fval(bn), w2d)) { ln.drop(bv); continue; }
-        break;
+  // Divide and conquer over the chunks: at level l the groups of 2^(l-1) chunks left and right
+  // of every boundary that is a multiple of 2^(l-1) but not of 2^l are merged, all boundaries
+  // of a level (and all lines) in parallel.  Left of a boundary stands the finished hull of the
+  // run's rows in the left group (A), right of it the finished hull of its rows in the right
+  // group (B).  All of A lies left of all of B, so the hull of the union is a prefix of A plus
+  // a suffix of B: drop A's top while it is hidden by (the vertex below it, B's first), drop
+  // B's first while it is hidden by (A's top, B's second), until neither applies.
+  int levels = 0;
+  while ((1 << levels) < nchunks) ++levels;
+  for (int lev = 1; lev <= levels; ++lev) {
+    const int half = 1 << (lev - 1);
+    if (live) {
+      for (int c = chunk0; c < nchunks; c += chunk_step) {
+        if ((c & ((half << 1) - 1)) != half) continue;     // c = first chunk of a right group
+        const int i0 = c << 5;
+        const uint32_t wc = lds_u32(startcol + (uint32_t)c * ROW);
+        if (wc & 1u) continue;                             // a run starts exactly here: nothing crosses
+        int a = 0;                                         // start of the run that crosses
+        for (int cc = c - 1; cc >= 0; --cc) {
+          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+          if (w) { a = (cc << 5) + 31 - __clz(w); break; }
+        }
+        int b = n;                                         // its end (exclusive)
+        for (int cc = c; cc < nchunks; ++cc) {
+          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+          if (w) { b = min(n, (cc << 5) + __ffs(w) - 1); break; }
+        }
+        const int alo = max(a, (c - half) << 5);           // the run's rows inside the two groups
+        const int bhi = min(b, min(n, (c + half) << 5));
+        int av = prev_vertex<TX>(ln, i0, alo);
+        int bv = next_vertex<TX>(ln, i0 - 1, bhi);
+        if (av < 0 || bv < 0) continue;
+        int ap = prev_vertex<TX>(ln, av, alo);
+        int bn = next_vertex<TX>(ln, bv, bhi);
+        float fa = ln.fval(av), fb = ln.fval(bv);
+        float fap = ap >= 0 ? ln.fval(ap) : 0.0f, fbn = bn >= 0 ? ln.fval(bn) : 0.0f;
+        for (;;) {
+          if (ap >= 0 && vertex_hidden(ap, fap, av, fa, bv, fb, w2d)) {         // A's top is hidden
+            ln.drop(av);
+            av = ap; fa = fap;
+            ap = prev_vertex<TX>(ln, av, alo);
+            if (ap >= 0) fap = ln.fval(ap);
+            continue;
+          }
+          if (bn >= 0 && vertex_hidden(av, fa, bv, fb, bn, fbn, w2d)) {         // B's first is hidden
+            ln.drop(bv);
+            bv = bn; fb = fbn;
+            bn = next_vertex<TX>(ln, bv, bhi);
+            if (bn >= 0) fbn = ln.fval(bn);
+            continue;
+          }
+          break;
+        }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   // ============ stage 3: outputs of the run segments that cross chunk boundaries ============
   if (live) {
