@@ -216,7 +216,8 @@ bool make_tile_map(CUtensorMap* map, float* f, const edtb200::LineGeom& g, int t
 // Shared memory of one tile of `tx` lines (see later_axis_tile_kernel).
 size_t tile_smem_bytes(int n, int tx, int rows_alloc) {
   const int nchunks = (n + 31) >> 5;
-  return (size_t)rows_alloc * tx * 4 + (size_t)nchunks * tx * 12 + (size_t)((n + 3) & ~1) * 4 + 16;
+  return (size_t)rows_alloc * tx * 4 + (size_t)nchunks * tx * 12 + (size_t)((n + 3) & ~1) * 4 + 16 +
+         (size_t)nchunks * tx;     // + one flag byte per (chunk, line)
 }
 
 template <int Bytes, int TX>

@@ -448,6 +448,14 @@ __device__ __forceinline__ uint32_t smem_token() {
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u8_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
@@ -608,6 +616,41 @@ __device__ __forceinline__ void read_out_local(const TileLine<TX> ln, uint32_t h
   }
 }
 
+// A long run [a, b) (more than 32 rows, so it spans chunk boundaries) is constant if each of its
+// chunk segments was found constant in stage 1 (flag bits, see the kernel) and all segments
+// share one value.  Then no scan is needed at all: out = min(f, border terms).
+template <int TX>
+__device__ __forceinline__ bool run_is_constant(const TileLine<TX> ln, uint32_t cflagcol, int a, int b) {
+  const int ca = a >> 5, cb = (b - 1) >> 5;
+  const float f0 = ln.fval(a);
+  if (!(lds_u8_volatile(cflagcol + (uint32_t)ca * TX) & 2u)) return false;      // segment leaving chunk ca
+  for (int c = ca + 1; c <= cb; ++c) {
+    if (!(lds_u8_volatile(cflagcol + (uint32_t)c * TX) & 1u)) return false;     // segment entering chunk c
+    if (!(ln.fval(c << 5) == f0)) return false;
+  }
+  return true;
+}
+
+template <int TX, bool Epilogue>
+__device__ __forceinline__ void write_constant_run(const TileLine<TX> ln, int lo, int hi, int a, int b,
+                                                   bool lo_border, bool hi_border, uint32_t sq,
+                                                   char* __restrict__ line0, size_t pitch, bool background,
+                                                   int flags) {
+  const float f0 = ln.fval(a);
+  char* dst = line0 + (size_t)lo * pitch;
+  uint32_t sq_lo = sq + (uint32_t)(lo - a + 1) * 4u;     // sq[i - a + 1]
+  uint32_t sq_hi = sq + (uint32_t)(b - lo) * 4u;         // sq[b - i]
+  for (int i = lo; i < hi; ++i) {
+    float best = f0;
+    if (lo_border) best = fminf(best, lds_f32(sq_lo));
+    if (hi_border) best = fminf(best, lds_f32(sq_hi));
+    sq_lo += 4u; sq_hi -= 4u;
+    if (Epilogue) best = finish_value(best, background, flags);
+    *reinterpret_cast<float*>(dst) = best;
+    dst += pitch;
+  }
+}
+
 // True if every sample of rows [sa, sb) equals the first one (returned in f0).  Equal-height
 // parabolas never hide one another, so a constant segment needs no envelope scan at all: every
 // row is its own best site and its value is min(f0, border terms).  This is the common case
@@ -686,6 +729,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   const uint32_t hullw_a = zerow_a + (uint32_t)nchunks * ROW;           // u32   [nchunks][TX]
   const uint32_t sq_a = hullw_a + (uint32_t)nchunks * ROW;              // float [n + 2]
   const uint32_t bar_a = sq_a + (uint32_t)((n + 2 + 1) & ~1) * 4u;      // mbarrier
+  const uint32_t cflag_a = bar_a + 16u;                                 // u8    [nchunks][TX]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_tile + (bar_a - fs_a));
 
   const int lane = threadIdx.x & 31;
@@ -762,6 +806,9 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   const uint32_t startcol = startw_a + (uint32_t)x * 4u + tok;
   const uint32_t zerocol = zerow_a + (uint32_t)x * 4u + tok;
   const uint32_t sq_t = sq_a + tok;
+  // per (chunk, line): bit 0 = the long-run segment entering from below is constant,
+  //                    bit 1 = the long-run segment leaving above is constant
+  const uint32_t cflagcol = cflag_a + (uint32_t)x;
   char* const line0 = reinterpret_cast<char*>(tf + x);
 
   // ============ stage 1: runs of length one; hulls of every other run, chunk by chunk ============
@@ -806,6 +853,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       // to the run start).  Longer runs only get the hull of their rows in this chunk, recorded in
       // hullw (bits relative to i0), and are stitched and read out in stages 2 and 3.
       uint32_t hb = 0u;
+      uint32_t cflags = 0u;
       const uint32_t todo = wstart & rowmask & ~single;
       int next_start = -1;                                 // first run start after this chunk (lazy)
       for (uint32_t rest = todo; rest;) {
@@ -849,6 +897,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
         } else {
           if (segment_constant<TX>(ln, sa, i0 + 32, f0)) {
             if (f0 < inf) hb |= 0xffffffffu << r0;            // every row is a vertex
+            cflags |= 2u;
           } else {
             hb = build_hull<TX>(ln, i0, sa, i0 + 32, w2d, hb);
           }
@@ -880,6 +929,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           float f0;
           if (segment_constant<TX>(ln, i0, seg_end, f0)) {
             if (f0 < inf) hb |= (seg_end - i0 == 32) ? 0xffffffffu : ((1u << (seg_end - i0)) - 1u);
+            cflags |= 1u;
           } else {
             hb = build_hull<TX>(ln, i0, i0, seg_end, w2d, hb);
           }
@@ -887,6 +937,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
         }
       }
       sts_u32(ln.hull + (uint32_t)c * ROW, hb);
+      sts_u8(cflagcol + (uint32_t)c * TX, cflags);
     }
   }
   if (!__syncthreads_or(crossing)) return;                 // every run was finished inside its chunk
@@ -918,6 +969,15 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
         for (int cc = c; cc < nchunks; ++cc) {
           const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
           if (w) { b = min(n, (cc << 5) + __ffs(w) - 1); break; }
+        }
+        if (lev == 1) {
+          // (first level only: later levels see hulls that earlier merges may have thinned out)
+          // equal-height rows on both sides of the boundary cannot hide one another: when the two
+          // adjacent chunk segments are constant and equal there is nothing to drop here
+          const uint32_t fl_hi = lds_u8_volatile(cflagcol + (uint32_t)c * TX);
+          const uint32_t fl_lo = lds_u8_volatile(cflagcol + (uint32_t)(c - 1) * TX);
+          const bool lo_const = (a >= ((c - 1) << 5)) ? (fl_lo & 2u) != 0 : (fl_lo & 1u) != 0;
+          if ((fl_hi & 1u) && lo_const && ln.fval(i0) == ln.fval(i0 - 1)) continue;
         }
         const int alo = max(a, (c - half) << 5);           // the run's rows inside the two groups
         const int bhi = min(b, min(n, (c + half) << 5));
@@ -980,16 +1040,26 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       if (open_lo) {
         const int hi = wreal ? (i0 + __ffs(wreal) - 1) : (i0 + rows);   // rows of this chunk in the run
         const int b = wreal ? hi : b_hi;
-        if (b - a_lo > 32)                                              // short runs were finished in stage 1
-          read_out<TX, Epilogue>(ln, i0, hi, a_lo, b, w2, a_lo > 0 || border_lo, b < n || border_hi, sq_t,
-                                 line0, pitch, wzero & 1u, flags);
+        if (b - a_lo > 32) {                                            // short runs were finished in stage 1
+          if (run_is_constant<TX>(ln, cflagcol, a_lo, b))
+            write_constant_run<TX, Epilogue>(ln, i0, hi, a_lo, b, a_lo > 0 || border_lo, b < n || border_hi, sq_t,
+                                             line0, pitch, wzero & 1u, flags);
+          else
+            read_out<TX, Epilogue>(ln, i0, hi, a_lo, b, w2, a_lo > 0 || border_lo, b < n || border_hi, sq_t,
+                                   line0, pitch, wzero & 1u, flags);
+        }
       }
       if (open_hi && wreal) {                                           // a run starting here and leaving above
         const int r0 = 31 - __clz(wreal);
         const int lo = i0 + r0;
-        if (b_hi - lo > 32)
-          read_out<TX, Epilogue>(ln, lo, i0 + 32, lo, b_hi, w2, lo > 0 || border_lo, b_hi < n || border_hi, sq_t,
-                                 line0, pitch, (wzero >> r0) & 1u, flags);
+        if (b_hi - lo > 32) {
+          if (run_is_constant<TX>(ln, cflagcol, lo, b_hi))
+            write_constant_run<TX, Epilogue>(ln, lo, i0 + 32, lo, b_hi, lo > 0 || border_lo, b_hi < n || border_hi,
+                                             sq_t, line0, pitch, (wzero >> r0) & 1u, flags);
+          else
+            read_out<TX, Epilogue>(ln, lo, i0 + 32, lo, b_hi, w2, lo > 0 || border_lo, b_hi < n || border_hi, sq_t,
+                                   line0, pitch, (wzero >> r0) & 1u, flags);
+        }
       }
     }
   }

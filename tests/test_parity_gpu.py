@@ -347,3 +347,32 @@ int main(int argc, char** argv) {
   sq = oracle.edtsq(lab, anisotropy=(2, 3, 5), black_border=True).ravel(order="F")
   assert np.array_equal(out[0], sq) and np.array_equal(out[2], sq)
   assert np.array_equal(out[1], oracle.edt(lab, anisotropy=(2, 3, 5), black_border=False).ravel(order="F"))
+
+
+def test_cfg4_1024_device_resident(edt):
+  """BASELINE.json configs[3] size (1024^3), entirely on the device (8 GiB resident): closed
+  form for the all-foreground box, and label-permutation / power-of-two scaling invariance for
+  iid uint32 labels (size-independent properties; the oracle would need minutes here)."""
+  import torch
+  n = 1024
+  dev = torch.device("cuda", 0)
+  ones = torch.ones((n, n, n), dtype=torch.uint8, device=dev)
+  got = edt.edt_cuda(ones, (3.0, 2.0, 1.0), True)
+  del ones
+  i = torch.arange(n, device=dev, dtype=torch.float32)
+  edge = torch.minimum(i + 1, n - i)
+  want = torch.minimum(torch.minimum(((3.0 * edge) ** 2).view(n, 1, 1), ((2.0 * edge) ** 2).view(1, n, 1)),
+                       (edge ** 2).view(1, 1, n))
+  assert bool((got == want).all())
+  del got, want
+  g = torch.Generator(device=dev)
+  g.manual_seed(0)
+  lab = torch.randint(0, 256, (n, n, n), dtype=torch.int32, device=dev, generator=g)
+  base = edt.edt_cuda(lab)
+  assert bool((base[lab == 0] == 0).all()) and float(base.max()) < 64.0
+  lut = torch.cat([torch.zeros(1, dtype=torch.int32, device=dev),
+                   (torch.randperm(255, device=dev, generator=g).to(torch.int32) + 1) * 16777259])
+  relabelled = lut[lab]
+  assert bool((edt.edt_cuda(relabelled) == base).all())
+  del relabelled
+  assert bool((edt.edt_cuda(lab, (4.0, 4.0, 4.0)) == base * 16.0).all())
