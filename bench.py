@@ -228,14 +228,11 @@ def ours(args):
     if rc != 0:
       raise RuntimeError(lib.edtb200_last_error().decode())
 
+  DEV_FLAGS = 4 | 8            # EDTB200_LABELS_ON_DEVICE | EDTB200_OUT_ON_DEVICE
+
   def step(events=None):
-    if events is not None: events[0].record(stream)
-    check(lib.edtb200_pass_first(lp, LABEL_BYTES, sx, sy, sz, ANISOTROPY[0], 0, 0, fp, local, sptr))
-    if events is not None: events[1].record(stream)
-    check(lib.edtb200_pass_later(lp, LABEL_BYTES, 1, sx, sy, sz, ANISOTROPY[1], 0, 0, 0, fp, local, sptr))
-    if events is not None: events[2].record(stream)
-    check(lib.edtb200_pass_later(lp, LABEL_BYTES, 2, sx, sy, sz, ANISOTROPY[2], 0, 0, 0, fp, local, sptr))
-    if events is not None: events[3].record(stream)
+    # one full transform through the public C-ABI entry point, device-resident, asynchronous
+    check(lib.edtb200_transform(lp, LABEL_BYTES, 3, sx, sy, sz, *ANISOTROPY, 0, DEV_FLAGS, fp, local, sptr))
 
   def barrier():
     if world > 1:
@@ -356,11 +353,20 @@ def ours(args):
     dist.destroy_process_group()
     return
 
-  # per-pass device times (same timed region) -> roofline of the dominant kernel
-  pass_ms = [statistics.mean(e[i].elapsed_time(e[i + 1]) for e in evs) for i in range(3)]
+  # per-pass device times -> roofline of the dominant kernel: the same transform, re-run with the
+  # library's pass events switched on (CUDA events recorded on the launch stream around each pass)
+  lib.edtb200_profile_passes(1)
+  samples = []
+  buf3 = (ctypes.c_float * 3)()
+  for _ in range(max(5, min(args.steps, 20))):
+    step()
+    check(lib.edtb200_last_pass_ms(ctypes.cast(buf3, ctypes.c_void_p)))
+    samples.append([float(buf3[0]), float(buf3[1]), float(buf3[2])])
+  lib.edtb200_profile_passes(0)
+  pass_ms = [statistics.mean(smp[i] for smp in samples) for i in range(3)]
   alg_bytes = [(LABEL_BYTES + 4) * nvox, (LABEL_BYTES + 8) * nvox, (LABEL_BYTES + 8) * nvox]
-  names = ["first_axis_vec_kernel<4,4,true> (X)", "later_axis_tile_kernel<4,32,false,true> (Y)",
-           "later_axis_tile_kernel<4,32,false,true> (Z)"]
+  names = ["first_axis_vec_kernel<4,4,true,false> (X)", "later_axis_tile_kernel<4,32,false,true,false> (Y)",
+           "later_axis_tile_kernel<4,32,false,true,false> (Z)"]
   dom = max(range(3), key=lambda i: pass_ms[i])
   achieved = alg_bytes[dom] / (pass_ms[dom] * 1e-3) / 1e9
   traffic = ncu_traffic()

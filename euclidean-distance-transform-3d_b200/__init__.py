@@ -74,6 +74,10 @@ def _lib():
   lib.edtb200_slab_face_runs.restype = ci
   lib.edtb200_slab_face_fixup.argtypes = [vp, ci, i64, i64, i64, ci, ci, f32, ci, vp, vp, vp, vp, ci, vp]
   lib.edtb200_slab_face_fixup.restype = ci
+  lib.edtb200_profile_passes.argtypes = [ci]
+  lib.edtb200_profile_passes.restype = ci
+  lib.edtb200_last_pass_ms.argtypes = [vp]
+  lib.edtb200_last_pass_ms.restype = ci
   lib.edtb200_release.restype = ci
   _LIB = lib
   return lib

@@ -91,6 +91,14 @@ int probe(int device, DeviceCache** out) {
   if (!dc.probed) {
     CUDA_TRY(cudaDeviceGetAttribute(&dc.sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&dc.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    // keep stream-ordered allocations (the code plane, long-line temporaries) in the pool between
+    // calls instead of returning them to the driver at every synchronisation
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     dc.probed = true;
   }
   *out = &dc;
@@ -141,9 +149,13 @@ int step_table(DeviceCache& dc, float w, int count, cudaStream_t stream, const f
 
 // ---- launches ---------------------------------------------------------------------
 
+// codes != nullptr asks for the one-byte neighbour codes (see first_axis_vec_kernel); *codes_done
+// reports whether they were produced (only the vector kernel can).
 template <int Bytes>
 int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float w, int border,
-                 int flags, DeviceCache& dc, cudaStream_t stream) {
+                 int flags, DeviceCache& dc, cudaStream_t stream, uint8_t* codes = nullptr, int64_t sy = 1,
+                 bool* codes_done = nullptr) {
+  if (codes_done) *codes_done = false;
   using namespace edtb200;
   const float* table = nullptr;
   int trc = step_table(dc, w, (int)sx + 1, stream, &table);
@@ -159,14 +171,24 @@ int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const LT* lab = static_cast<const LT*>(labels);
+    const bool want_codes = codes != nullptr && reinterpret_cast<uintptr_t>(codes) % 4 == 0;
 #define EDT_LAUNCH_VEC(KK)                                                                         \
   do {                                                                                           \
-    if (flags == 0)                                                                              \
-      first_axis_vec_kernel<Bytes, KK, true><<<(unsigned)blocks, 256, smem, stream>>>(            \
-          lab, f, nlines, (int)sx, table, border, flags);                                        \
-    else                                                                                         \
-      first_axis_vec_kernel<Bytes, KK, false><<<(unsigned)blocks, 256, smem, stream>>>(           \
-          lab, f, nlines, (int)sx, table, border, flags);                                        \
+    if (want_codes) {                                                                            \
+      if (flags == 0)                                                                            \
+        first_axis_vec_kernel<Bytes, KK, true, true><<<(unsigned)blocks, 256, smem, stream>>>(    \
+            lab, f, nlines, (int)sx, table, border, flags, codes, (int)sy);                      \
+      else                                                                                       \
+        first_axis_vec_kernel<Bytes, KK, false, true><<<(unsigned)blocks, 256, smem, stream>>>(   \
+            lab, f, nlines, (int)sx, table, border, flags, codes, (int)sy);                      \
+    } else {                                                                                     \
+      if (flags == 0)                                                                            \
+        first_axis_vec_kernel<Bytes, KK, true, false><<<(unsigned)blocks, 256, smem, stream>>>(   \
+            lab, f, nlines, (int)sx, table, border, flags, nullptr, 1);                          \
+      else                                                                                       \
+        first_axis_vec_kernel<Bytes, KK, false, false><<<(unsigned)blocks, 256, smem, stream>>>(  \
+            lab, f, nlines, (int)sx, table, border, flags, nullptr, 1);                          \
+    }                                                                                            \
   } while (0)
     if (sx <= 128)      EDT_LAUNCH_VEC(1);
     else if (sx <= 256) EDT_LAUNCH_VEC(2);
@@ -174,6 +196,7 @@ int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float
     else                EDT_LAUNCH_VEC(8);
 #undef EDT_LAUNCH_VEC
     CUDA_TRY(cudaGetLastError());
+    if (codes_done) *codes_done = want_codes;
     return 0;
   }
   const int nwords = (int)(sx >> 5) + 1;
@@ -222,7 +245,7 @@ size_t tile_smem_bytes(int n, int tx, int rows_alloc) {
 
 template <int Bytes, int TX>
 int launch_tile(const void* labels, float* f, edtb200::LineGeom g, float w2, int border_lo, int border_hi,
-                int flags, bool use_tma, cudaStream_t stream) {
+                int flags, bool use_tma, cudaStream_t stream, int code_bit = 0) {
   using namespace edtb200;
   using LT = typename LabelOf<Bytes>::type;
   const int nchunks = (g.n + 31) >> 5;
@@ -242,22 +265,33 @@ int launch_tile(const void* labels, float* f, edtb200::LineGeom g, float w2, int
   int warps = (nchunks + SUBS - 1) / SUBS;
   if (warps > 16) warps = 16;
   const LT* lab = static_cast<const LT*>(labels);
-#define EDT_LAUNCH_TILE(EPI, TMA)                                                                   \
+#define EDT_LAUNCH_TILE(EPI, TMA, CODES)                                                            \
   do {                                                                                              \
-    auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA>;                                        \
+    auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, CODES>;                                 \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, lab, f, g, tb, w2, border_lo, border_hi, flags); \
+    kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, lab, f, g, tb, w2, border_lo, border_hi, flags, \
+                                                        code_bit);                                  \
   } while (0)
-  if (flags) { if (use_tma) EDT_LAUNCH_TILE(true, true); else EDT_LAUNCH_TILE(true, false); }
-  else       { if (use_tma) EDT_LAUNCH_TILE(false, true); else EDT_LAUNCH_TILE(false, false); }
+  if constexpr (Bytes == 1) {
+    if (code_bit) {
+      if (flags) { if (use_tma) EDT_LAUNCH_TILE(true, true, true); else EDT_LAUNCH_TILE(true, false, true); }
+      else       { if (use_tma) EDT_LAUNCH_TILE(false, true, true); else EDT_LAUNCH_TILE(false, false, true); }
+      CUDA_TRY(cudaGetLastError());
+      return 0;
+    }
+  }
+  if (flags) { if (use_tma) EDT_LAUNCH_TILE(true, true, false); else EDT_LAUNCH_TILE(true, false, false); }
+  else       { if (use_tma) EDT_LAUNCH_TILE(false, true, false); else EDT_LAUNCH_TILE(false, false, false); }
 #undef EDT_LAUNCH_TILE
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
+// code_bit != 0: `labels` are the one-byte codes of the first-axis pass (Bytes must be 1); the
+// caller must have checked tile_path_ok() because only the tile kernel understands codes.
 template <int Bytes>
 int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, float w, int border_lo,
-                 int border_hi, int flags, const DeviceCache& dc, cudaStream_t stream) {
+                 int border_hi, int flags, const DeviceCache& dc, cudaStream_t stream, int code_bit = 0) {
   using namespace edtb200;
   using LT = typename LabelOf<Bytes>::type;
   LineGeom g = g0;
@@ -280,12 +314,13 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
     if (tx) {
       const bool use_tma = aligned && g.inner_count >= tx;
       switch (tx) {
-        case 32: return launch_tile<Bytes, 32>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream);
-        case 16: return launch_tile<Bytes, 16>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream);
-        default: return launch_tile<Bytes, 8>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream);
+        case 32: return launch_tile<Bytes, 32>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit);
+        case 16: return launch_tile<Bytes, 16>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit);
+        default: return launch_tile<Bytes, 8>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit);
       }
     }
   }
+  if (code_bit) return fail(EDTB200_ELIMIT, "internal: neighbour codes need the tile kernel");
   // ---- lines too long for a shared-memory tile: out of place through a temporary volume ----
   const int64_t lines = g.inner_count * g.outer_count;
   const size_t bytes = sizeof(float) * (size_t)lines * (size_t)g.n;
@@ -302,19 +337,29 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
 }
 
 int dispatch_first(int label_bytes, const void* labels, float* f, int64_t nlines, int64_t sx, float w,
-                   int border, int flags, DeviceCache& dc, cudaStream_t s) {
+                   int border, int flags, DeviceCache& dc, cudaStream_t s, uint8_t* codes = nullptr,
+                   int64_t sy = 1, bool* codes_done = nullptr) {
   switch (label_bytes) {
-    case 1: return launch_first<1>(labels, f, nlines, sx, w, border, flags, dc, s);
-    case 2: return launch_first<2>(labels, f, nlines, sx, w, border, flags, dc, s);
-    case 4: return launch_first<4>(labels, f, nlines, sx, w, border, flags, dc, s);
-    default: return launch_first<8>(labels, f, nlines, sx, w, border, flags, dc, s);
+    case 1: return launch_first<1>(labels, f, nlines, sx, w, border, flags, dc, s, codes, sy, codes_done);
+    case 2: return launch_first<2>(labels, f, nlines, sx, w, border, flags, dc, s, codes, sy, codes_done);
+    case 4: return launch_first<4>(labels, f, nlines, sx, w, border, flags, dc, s, codes, sy, codes_done);
+    default: return launch_first<8>(labels, f, nlines, sx, w, border, flags, dc, s, codes, sy, codes_done);
   }
 }
 
+// Will launch_later() take the shared-memory tile kernel for this geometry?  (same conditions)
+bool tile_path_ok(const edtb200::LineGeom& g, const DeviceCache& dc) {
+  if (!((int64_t)g.n * g.line_stride + 64 < (1LL << 32) && g.n <= 4096 && g.inner_count < (1LL << 31))) return false;
+  const int nb = (g.n + 255) / 256;
+  int br = (g.n + nb - 1) / nb;
+  if (nb > 1) br = (br + 3) & ~3;
+  return tile_smem_bytes(g.n, 8, br * nb) <= (size_t)dc.max_smem_optin;
+}
+
 int dispatch_later(int label_bytes, const void* labels, float* f, const edtb200::LineGeom& g, float w,
-                   int lo, int hi, int flags, const DeviceCache& dc, cudaStream_t s) {
+                   int lo, int hi, int flags, const DeviceCache& dc, cudaStream_t s, int code_bit = 0) {
   switch (label_bytes) {
-    case 1: return launch_later<1>(labels, f, g, w, lo, hi, flags, dc, s);
+    case 1: return launch_later<1>(labels, f, g, w, lo, hi, flags, dc, s, code_bit);
     case 2: return launch_later<2>(labels, f, g, w, lo, hi, flags, dc, s);
     case 4: return launch_later<4>(labels, f, g, w, lo, hi, flags, dc, s);
     default: return launch_later<8>(labels, f, g, w, lo, hi, flags, dc, s);
@@ -332,14 +377,17 @@ edtb200::LineGeom geom_for_axis(int axis, int64_t sx, int64_t sy, int64_t sz) {
   return g;
 }
 
-// Bytes of (labels + distances) per X/Y slab; 0 disables slabbing.  EDTB200_XY_SLAB_MB overrides.
-int64_t xy_slab_bytes() {
-  static int64_t cached = -1;
-  if (cached < 0) {
-    const char* env = getenv("EDTB200_XY_SLAB_MB");
-    cached = (env ? atoll(env) : 0) * (int64_t)(1 << 20);
-  }
-  return cached;
+// Optional per-pass timing for bench.py: four events recorded around the three passes of the
+// most recent transform on this thread (see edtb200_profile_passes / edtb200_last_pass_ms).
+thread_local bool g_profile = false;
+thread_local cudaEvent_t g_pass_events[4] = {nullptr, nullptr, nullptr, nullptr};
+thread_local int g_pass_count = 0;
+
+void mark_pass(int idx, cudaStream_t stream) {
+  if (!g_profile) return;
+  if (!g_pass_events[idx] && cudaEventCreate(&g_pass_events[idx]) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaEventRecord(g_pass_events[idx], stream);
+  g_pass_count = idx;
 }
 
 // All passes of one transform on device-resident buffers.
@@ -351,42 +399,38 @@ int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_
   // changes the first pass only -- later passes treat every run alike.
   const int epilogue = ((flags & EDTB200_SQRT) ? kSqrt : 0) | ((flags & EDTB200_SIGNED) ? kNegate : 0);
   const int zero_label = (flags & EDTB200_SIGNED) ? kZeroLabel : 0;
+  // EXPERIMENT, off by default (EDTB200_USE_CODES=1 turns it on): read labels wider than one byte
+  // ONCE -- the first-axis pass leaves a one-byte code per voxel (differs from its y / z
+  // neighbour, is background) and the later passes read that instead (3L+20 -> L+22 bytes per
+  // voxel of HBM traffic).  Measured on B200, 512^3 uint32: Y 0.261 -> 0.244 ms, Z 0.280 -> 0.250 ms,
+  // but the first-axis pass 0.180 -> 0.350 ms (two more label rows through L2 + 75 registers), a
+  // net loss (0.84 vs 0.73 ms), so the passes read the labels by default.
   int rc = 0;
-  if (ndim < 3) {
-    rc = dispatch_first(label_bytes, labels, f, sy * sz, sx, wx, border,
-                        zero_label | (ndim == 1 ? epilogue : 0), dc, stream);
-    if (rc) return rc;
-    if (ndim == 2) {
-      rc = dispatch_later(label_bytes, labels, f, geom_for_axis(1, sx, sy, sz), wy, border, border,
-                          epilogue, dc, stream);
-      if (rc) return rc;
-    }
-    return 0;
+  uint8_t* codes = nullptr;
+  bool codes_done = false;
+  const edtb200::LineGeom gy = geom_for_axis(1, sx, sy, sz), gz = geom_for_axis(2, sx, sy, sz);
+  static const bool codes_enabled = getenv("EDTB200_USE_CODES") != nullptr;
+  if (codes_enabled && label_bytes > 1 && ndim >= 2 && tile_path_ok(gy, dc) && (ndim < 3 || tile_path_ok(gz, dc)))
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&codes), (size_t)(sx * sy * sz), stream));
+  mark_pass(0, stream);
+  rc = dispatch_first(label_bytes, labels, f, sy * sz, sx, wx, border, zero_label | (ndim == 1 ? epilogue : 0), dc,
+                      stream, codes, sy, &codes_done);
+  mark_pass(1, stream);
+  if (!rc && ndim >= 2) {
+    rc = codes_done ? dispatch_later(1, codes, f, gy, wy, border, border, ndim == 2 ? epilogue : 0, dc, stream, 1)
+                    : dispatch_later(label_bytes, labels, f, gy, wy, border, border, ndim == 2 ? epilogue : 0, dc,
+                                     stream, 0);
+    mark_pass(2, stream);
   }
-  // 3-D: the X and Y passes only couple voxels of one z-slice, so they are run slab by slab
-  // (X then Y on the same few slices) with slabs sized to stay resident in the 126 MB L2:
-  // the Y pass then finds the labels and the X pass's distances in L2 and HBM sees the label
-  // slab once and the distance slab once (written after Y) instead of 5 voxel-sized streams.
-  const int64_t slice_bytes = sx * sy * (int64_t)(label_bytes + 4);
-  int64_t slab = xy_slab_bytes() / (slice_bytes > 0 ? slice_bytes : 1);
-  if (slab < 1) slab = 1;
-  if (xy_slab_bytes() <= 0 || slab > sz) slab = sz;
-  for (int64_t z0 = 0; z0 < sz; z0 += slab) {
-    const int64_t zc = (sz - z0 < slab) ? (sz - z0) : slab;
-    const char* lab0 = static_cast<const char*>(labels) + z0 * sx * sy * label_bytes;
-    float* f0 = f + z0 * sx * sy;
-    rc = dispatch_first(label_bytes, lab0, f0, sy * zc, sx, wx, border, zero_label, dc, stream);
-    if (rc) return rc;
-    rc = dispatch_later(label_bytes, lab0, f0, geom_for_axis(1, sx, sy, zc), wy, border, border, 0, dc, stream);
-    if (rc) return rc;
+  if (!rc && ndim >= 3) {
+    rc = codes_done ? dispatch_later(1, codes, f, gz, wz, border, border, epilogue, dc, stream, 2)
+                    : dispatch_later(label_bytes, labels, f, gz, wz, border, border, epilogue, dc, stream, 0);
+    mark_pass(3, stream);
   }
-  if (ndim >= 3) {
-    rc = dispatch_later(label_bytes, labels, f, geom_for_axis(2, sx, sy, sz), wz, border, border,
-                        epilogue, dc, stream);
-    if (rc) return rc;
-  }
-  return 0;
+  if (codes) cudaFreeAsync(codes, stream);
+  return rc;
 }
+
 
 }  // namespace
 
@@ -547,6 +591,22 @@ int edtb200_slab_face_fixup(const void* labels_dev, int label_bytes, int64_t sx,
     default: face_fixup_kernel<8><<<blocks, 256, 0, stream>>>(static_cast<const uint64_t*>(labels_dev), f_dev, plane, (int)sz, high_face, halo, w2, static_cast<const uint64_t*>(nb_label_dev), nb_m_dev, nb_f_dev, kflags); break;
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int edtb200_profile_passes(int enable) {
+  g_profile = enable != 0;
+  return 0;
+}
+
+int edtb200_last_pass_ms(float* ms3) {
+  if (!ms3) return fail(EDTB200_EINVAL, "null pointer");
+  ms3[0] = ms3[1] = ms3[2] = 0.0f;
+  for (int i = 0; i < g_pass_count && i < 3; ++i) {
+    if (!g_pass_events[i] || !g_pass_events[i + 1]) break;
+    CUDA_TRY(cudaEventSynchronize(g_pass_events[i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms3[i], g_pass_events[i], g_pass_events[i + 1]));
+  }
   return 0;
 }
 

@@ -218,11 +218,17 @@ template <> struct Vec4Labels<8> {
 
 // Plain = true: squared EDT, background forced to 0, no sqrt / sign (the hot configuration);
 // Plain = false: behaviour selected by `flags` at run time.
-template <int Bytes, int K, bool Plain>
+// Codes = true: additionally emit one byte per voxel for the later-axis passes, so that they
+// need not read the (wider) labels again:  bit 0 = label differs from (x, y-1, z),
+// bit 1 = label differs from (x, y, z-1), bit 2 = label is background.  The two neighbour rows
+// were read moments ago by neighbouring warps (row y-1) / the previous slice (z-1, 1 MiB back
+// at 512^2), i.e. they come from L1/L2, not from HBM.
+template <int Bytes, int K, bool Plain, bool Codes>
 __global__ void __launch_bounds__(256)
 first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
                       float* __restrict__ out, int64_t nlines, int sx,
-                      const float* __restrict__ table, int border, int flags) {
+                      const float* __restrict__ table, int border, int flags,
+                      uint8_t* __restrict__ codes, int sy) {
   using LT = typename LabelOf<Bytes>::type;
   using WT = typename LabelOf<Bytes>::wide;
   extern __shared__ float table_s[];                 // T[0..sx], then +inf at sx + 1
@@ -275,6 +281,30 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
       occ[b] = __ballot_sync(full, m != 0);
       edges |= m << (4 * b);
       zeros |= z << (4 * b);
+    }
+
+    if (Codes) {
+      const int64_t zi = line / sy;
+      const int yi = (int)(line - zi * sy);
+      uint8_t* __restrict__ crow = codes + line * sx;
+#pragma unroll
+      for (int b = 0; b < K; ++b) {
+        const int q0 = (b << 7) + (lane << 2);
+        if (q0 >= sx) continue;
+        WT up[4], dn[4];
+        if (yi > 0) Vec4Labels<Bytes>::load(src - sx + q0, up);
+        if (zi > 0) Vec4Labels<Bytes>::load(src - (int64_t)sx * sy + q0, dn);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint32_t cde = 0;
+          if (yi > 0 && up[e] != v[b][e]) cde |= 1u;
+          if (zi > 0 && dn[e] != v[b][e]) cde |= 2u;
+          if (v[b][e] == 0) cde |= 4u;
+          packed |= cde << (8 * e);
+        }
+        *reinterpret_cast<uint32_t*>(crow + q0) = packed;
+      }
     }
 
     // ---- nearest boundary strictly below / above the lane's 4 voxels, per block ----
@@ -708,12 +738,14 @@ __device__ __forceinline__ uint32_t build_hull(const TileLine<TX> ln, int o, int
   return hb;
 }
 
-template <int Bytes, int TX, bool Epilogue, bool UseTMA>
+// FromCodes = true: `labels` holds the one-byte codes written by first_axis_vec_kernel<..., Codes>
+// (Bytes = 1) and `code_bit` selects the axis (1 = y neighbour, 2 = z neighbour).
+template <int Bytes, int TX, bool Epilogue, bool UseTMA, bool FromCodes>
 __global__ void __launch_bounds__(512, 3)      // 3 CTAs of 512 threads per SM: at most 42 registers
 later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
                        const typename LabelOf<Bytes>::type* __restrict__ labels,
                        float* __restrict__ f, LineGeom g, TileBoxes tb, float w2,
-                       int border_lo, int border_hi, int flags) {
+                       int border_lo, int border_hi, int flags, int code_bit) {
   using LT = typename LabelOf<Bytes>::type;
   extern __shared__ __align__(128) unsigned char smem_tile[];
   constexpr int SUBS = 32 / TX;                       // chunks handled side by side by one warp
@@ -766,7 +798,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
     uint32_t wstart = 0, wzero = 0;
     if (live) {
       uint32_t idx = (uint32_t)i0 * ls + (uint32_t)x;
-      LT prev = (i0 > 0) ? tl[idx - ls] : (LT)0;
+      LT prev = (!FromCodes && i0 > 0) ? tl[idx - ls] : (LT)0;
       uint32_t fdst = fs_a + (uint32_t)i0 * ROW + (uint32_t)x * 4u;
       if (i0 + 32 <= n) {
 #pragma unroll
@@ -774,18 +806,28 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           const LT here = tl[idx];
           if (!UseTMA) sts_f32(fdst + r * ROW, tf[idx]);
           idx += ls;
-          if (here != prev) wstart |= (1u << r);
-          if (Epilogue && here == 0) wzero |= (1u << r);
-          prev = here;
+          if (FromCodes) {
+            if (here & code_bit) wstart |= (1u << r);
+            if (Epilogue && (here & 4)) wzero |= (1u << r);
+          } else {
+            if (here != prev) wstart |= (1u << r);
+            if (Epilogue && here == 0) wzero |= (1u << r);
+            prev = here;
+          }
         }
       } else {
         for (int r = 0; r < n - i0; ++r) {
           const LT here = tl[idx];
           if (!UseTMA) sts_f32(fdst + r * ROW, tf[idx]);
           idx += ls;
-          if (here != prev) wstart |= (1u << r);
-          if (Epilogue && here == 0) wzero |= (1u << r);
-          prev = here;
+          if (FromCodes) {
+            if (here & code_bit) wstart |= (1u << r);
+            if (Epilogue && (here & 4)) wzero |= (1u << r);
+          } else {
+            if (here != prev) wstart |= (1u << r);
+            if (Epilogue && here == 0) wzero |= (1u << r);
+            prev = here;
+          }
         }
         wstart |= 1u << (n - i0);          // pretend a run starts at row n (line end)
       }
