@@ -11,7 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -77,6 +81,151 @@ struct DeviceCache {
 
 std::mutex g_mutex;
 DeviceCache g_cache[kMaxDevices];
+
+// ---- host <-> device staging for pageable host memory --------------------------------
+// numpy arrays are pageable: a plain cudaMemcpy of 512 MiB then runs at a fraction of the PCIe
+// rate (the driver stages it through small internal buffers, and a freshly allocated output
+// array is also page-faulted in by that single thread).  Pinned callers are copied directly;
+// pageable ones go through three 32 MiB pinned buffers that a few host threads fill / drain in
+// parallel while the DMA engine moves the previous chunk.
+class CopyPool {
+ public:
+  explicit CopyPool(int n) : n_(n) {
+    for (int i = 0; i < n_; ++i) threads_.emplace_back([this, i] { loop(i); });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; ++epoch_; }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  int size() const { return n_; }
+  // run fn(i) for i in [0, n) on the pool and wait
+  void run(const std::function<void(int)>& fn) {
+    std::unique_lock<std::mutex> l(m_);
+    fn_ = &fn; pending_ = n_; ++epoch_;
+    cv_.notify_all();
+    done_.wait(l, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+ private:
+  void loop(int i) {
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) return;
+        fn = fn_;
+      }
+      (*fn)(i);
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  int n_;
+  std::vector<std::thread> threads_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int pending_ = 0;
+  unsigned long epoch_ = 0;
+  bool stop_ = false;
+};
+
+CopyPool* g_pool = nullptr;           // created on first use, under g_mutex
+
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  if (!g_pool) {
+    unsigned hw = std::thread::hardware_concurrency();
+    g_pool = new CopyPool(hw >= 16 ? 8 : (hw >= 4 ? 4 : 1));
+  }
+  const int n = g_pool->size();
+  const size_t slice = ((bytes + n - 1) / n + 4095) & ~size_t(4095);
+  g_pool->run([&](int i) {
+    const size_t off = slice * (size_t)i;
+    if (off < bytes) memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off,
+                            bytes - off < slice ? bytes - off : slice);
+  });
+}
+
+constexpr size_t kStageBytes = size_t(32) << 20;
+constexpr int kStages = 3;
+struct StageBuffers {
+  void* buf[kStages] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev[kStages] = {nullptr, nullptr, nullptr};
+};
+StageBuffers g_stage[kMaxDevices];
+
+bool host_pointer_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+int ensure_stage(int device) {
+  StageBuffers& sb = g_stage[device];
+  for (int i = 0; i < kStages; ++i) {
+    if (!sb.buf[i]) CUDA_TRY(cudaHostAlloc(&sb.buf[i], kStageBytes, cudaHostAllocDefault));
+    if (!sb.ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&sb.ev[i], cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+// host (pageable or pinned) -> device, stream-ordered; returns after the last chunk is queued
+int upload(void* dst_dev, const void* src_host, size_t bytes, int device, cudaStream_t stream) {
+  if (bytes < (size_t(4) << 20) || host_pointer_is_pinned(src_host)) {
+    CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream));
+    return 0;
+  }
+  int rc = ensure_stage(device);
+  if (rc) return rc;
+  StageBuffers& sb = g_stage[device];
+  size_t off = 0;
+  for (int k = 0; off < bytes; ++k) {
+    const int b = k % kStages;
+    const size_t n = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+    if (k >= kStages) CUDA_TRY(cudaEventSynchronize(sb.ev[b]));      // DMA out of this buffer finished
+    parallel_memcpy(sb.buf[b], static_cast<const char*>(src_host) + off, n);
+    CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dst_dev) + off, sb.buf[b], n, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaEventRecord(sb.ev[b], stream));
+    off += n;
+  }
+  return 0;
+}
+
+// device -> host (pageable or pinned); complete on return for the pageable case
+int download(void* dst_host, const void* src_dev, size_t bytes, int device, cudaStream_t stream) {
+  if (bytes < (size_t(4) << 20) || host_pointer_is_pinned(dst_host)) {
+    CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
+    return 0;
+  }
+  int rc = ensure_stage(device);
+  if (rc) return rc;
+  StageBuffers& sb = g_stage[device];
+  size_t off = 0, prev_off = 0, prev_n = 0;
+  int prev_b = -1;
+  for (int k = 0; off < bytes || prev_b >= 0; ++k) {
+    int b = -1;
+    size_t n = 0;
+    if (off < bytes) {
+      b = k % kStages;
+      n = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+      CUDA_TRY(cudaMemcpyAsync(sb.buf[b], static_cast<const char*>(src_dev) + off, n, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaEventRecord(sb.ev[b], stream));
+    }
+    if (prev_b >= 0) {                                             // drain the chunk queued one step earlier
+      CUDA_TRY(cudaEventSynchronize(sb.ev[prev_b]));
+      parallel_memcpy(static_cast<char*>(dst_host) + prev_off, sb.buf[prev_b], prev_n);
+    }
+    prev_b = b; prev_off = off; prev_n = n;
+    off += n;
+  }
+  return 0;
+}
 
 int probe(int device, DeviceCache** out) {
   if (device < 0 || device >= kMaxDevices) return fail(EDTB200_EINVAL, "bad device %d", device);
@@ -263,14 +412,22 @@ int launch_tile(const void* labels, float* f, edtb200::LineGeom g, float w2, int
   const size_t smem = tile_smem_bytes(g.n, TX, rows_alloc);
   constexpr int SUBS = 32 / TX;
   int warps = (nchunks + SUBS - 1) / SUBS;
-  if (warps > 16) warps = 16;
+  const bool wide = warps > 16;                 // long lines: one tile per SM, so give it 32 warps
+  if (warps > 32) warps = 32;
   const LT* lab = static_cast<const LT*>(labels);
 #define EDT_LAUNCH_TILE(EPI, TMA, CODES)                                                            \
   do {                                                                                              \
-    auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, CODES>;                                 \
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, lab, f, g, tb, w2, border_lo, border_hi, flags, \
-                                                        code_bit);                                  \
+    if (wide) {                                                                                     \
+      auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, CODES, true>;                         \
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, lab, f, g, tb, w2, border_lo, border_hi, flags, \
+                                                          code_bit);                                \
+    } else {                                                                                        \
+      auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, CODES, false>;                        \
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, lab, f, g, tb, w2, border_lo, border_hi, flags, \
+                                                          code_bit);                                \
+    }                                                                                               \
   } while (0)
   if constexpr (Bytes == 1) {
     if (code_bit) {
@@ -484,7 +641,8 @@ int edtb200_transform(const void* labels, int label_bytes, int ndim, int64_t sx,
       CUDA_TRY(cudaMalloc(&dc->labels, lab_bytes));
       dc->labels_bytes = lab_bytes;
     }
-    CUDA_TRY(cudaMemcpyAsync(dc->labels, labels, lab_bytes, cudaMemcpyHostToDevice, stream));
+    rc = upload(dc->labels, labels, lab_bytes, device, stream);
+    if (rc) return rc;
     d_labels = dc->labels;
   }
   if (!out_dev) {
@@ -498,7 +656,10 @@ int edtb200_transform(const void* labels, int label_bytes, int ndim, int64_t sx,
   }
   rc = run_passes(d_labels, label_bytes, ndim, sx, sy, sz, wx, wy, wz, border, flags, d_out, *dc, stream);
   if (rc) return rc;
-  if (!out_dev) CUDA_TRY(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+  if (!out_dev) {
+    rc = download(out, d_out, out_bytes, device, stream);
+    if (rc) return rc;
+  }
   CUDA_TRY(cudaStreamSynchronize(stream));
   return 0;
 }
@@ -626,6 +787,13 @@ int edtb200_release(void) {
     if (dc.labels) cudaFree(dc.labels);
     if (dc.dist) cudaFree(dc.dist);
     dc = DeviceCache();
+  }
+  for (int d = 0; d < count && d < kMaxDevices; ++d) {
+    StageBuffers& sb = g_stage[d];
+    for (int i = 0; i < kStages; ++i) {
+      if (sb.buf[i]) { cudaFreeHost(sb.buf[i]); sb.buf[i] = nullptr; }
+      if (sb.ev[i]) { cudaEventDestroy(sb.ev[i]); sb.ev[i] = nullptr; }
+    }
   }
   return 0;
 }

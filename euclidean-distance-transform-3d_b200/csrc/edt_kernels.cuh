@@ -740,8 +740,10 @@ __device__ __forceinline__ uint32_t build_hull(const TileLine<TX> ln, int o, int
 
 // FromCodes = true: `labels` holds the one-byte codes written by first_axis_vec_kernel<..., Codes>
 // (Bytes = 1) and `code_bit` selects the axis (1 = y neighbour, 2 = z neighbour).
-template <int Bytes, int TX, bool Epilogue, bool UseTMA, bool FromCodes>
-__global__ void __launch_bounds__(512, 3)      // 3 CTAs of 512 threads per SM: at most 42 registers
+// Wide = false: up to 16 warps per CTA, register budget for 3 CTAs per SM (lines <= 512 voxels fit
+// three tiles per SM).  Wide = true: up to 32 warps for long lines, whose tile fills an SM alone.
+template <int Bytes, int TX, bool Epilogue, bool UseTMA, bool FromCodes, bool Wide>
+__global__ void __launch_bounds__(Wide ? 1024 : 512, Wide ? 1 : 3)
 later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
                        const typename LabelOf<Bytes>::type* __restrict__ labels,
                        float* __restrict__ f, LineGeom g, TileBoxes tb, float w2,
