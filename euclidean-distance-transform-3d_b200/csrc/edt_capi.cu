@@ -227,6 +227,14 @@ int download(void* dst_host, const void* src_dev, size_t bytes, int device, cuda
   return 0;
 }
 
+// Restores the calling thread's current CUDA device when an entry point returns (callers such as
+// PyTorch rely on "their" current device staying put).
+struct DeviceGuard {
+  int saved = -1;
+  DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); saved = -1; } }
+  ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 int probe(int device, DeviceCache** out) {
   if (device < 0 || device >= kMaxDevices) return fail(EDTB200_EINVAL, "bad device %d", device);
   int count = 0;
@@ -613,6 +621,7 @@ int edtb200_transform(const void* labels, int label_bytes, int ndim, int64_t sx,
   if (!labels || !out) return fail(EDTB200_EINVAL, "null pointer");
 
   std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
   if (rc) return rc;
@@ -671,6 +680,7 @@ int edtb200_pass_first(const void* labels_dev, int label_bytes, int64_t sx, int6
   if (sx * sy * sz == 0) return 0;
   if (!labels_dev || !f_dev) return fail(EDTB200_EINVAL, "null pointer");
   std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
   if (rc) return rc;
@@ -689,6 +699,7 @@ int edtb200_pass_later(const void* labels_dev, int label_bytes, int axis, int64_
   if (sx * sy * sz == 0) return 0;
   if (!labels_dev || !f_dev) return fail(EDTB200_EINVAL, "null pointer");
   std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
   if (rc) return rc;
@@ -708,6 +719,7 @@ int edtb200_slab_face_runs(const void* labels_dev, int label_bytes, int64_t sx, 
   if (sx * sy * sz == 0) return 0;
   if (!labels_dev || !m_dev || !overflow_dev) return fail(EDTB200_EINVAL, "null pointer");
   std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
   if (rc) return rc;
@@ -736,6 +748,7 @@ int edtb200_slab_face_fixup(const void* labels_dev, int label_bytes, int64_t sx,
   if (sx * sy * sz == 0) return 0;
   if (!labels_dev || !nb_label_dev || !nb_m_dev || !nb_f_dev || !f_dev) return fail(EDTB200_EINVAL, "null pointer");
   std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
   if (rc) return rc;
@@ -773,6 +786,7 @@ int edtb200_last_pass_ms(float* ms3) {
 
 int edtb200_release(void) {
   std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceGuard restore_device;
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
   for (int d = 0; d < count && d < kMaxDevices; ++d) {

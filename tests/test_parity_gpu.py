@@ -376,3 +376,27 @@ def test_cfg4_1024_device_resident(edt):
   assert bool((edt.edt_cuda(relabelled) == base).all())
   del relabelled
   assert bool((edt.edt_cuda(lab, (4.0, 4.0, 4.0)) == base * 16.0).all())
+
+
+def test_current_device_and_threads(edt, oracle):
+  """The library must leave the caller's current CUDA device alone and survive concurrent calls."""
+  import threading
+  import torch
+  before = torch.cuda.current_device()
+  rng = np.random.default_rng(31)
+  labs = [cases.random_volume(rng, (40, 33, 29), kind, np.uint16) for kind in ("blocks", "iid", "balls", "few")]
+  want = [oracle.edtsq(l, anisotropy=(1, 2, 3), black_border=True) for l in labs]
+  got = [None] * len(labs)
+
+  def work(i):
+    for _ in range(3):
+      got[i] = edt.edtsq(labs[i], anisotropy=(1, 2, 3), black_border=True)
+
+  threads = [threading.Thread(target=work, args=(i,)) for i in range(len(labs))]
+  for t in threads:
+    t.start()
+  for t in threads:
+    t.join()
+  for g, w in zip(got, want):
+    assert_same(g, w, "concurrent")
+  assert torch.cuda.current_device() == before
