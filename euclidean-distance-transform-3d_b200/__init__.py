@@ -29,7 +29,7 @@ __version__ = "0.1.0"
 __all__ = [
   "edt", "edtsq", "sdf", "sdfsq",
   "edt1d", "edt1dsq", "edt2d", "edt2dsq", "edt3d", "edt3dsq",
-  "edt_cuda", "device_count", "library_path", "EDTError",
+  "edt_cuda", "each", "each_cuda", "device_count", "library_path", "EDTError",
 ]
 
 FLAG_SQRT = 1
@@ -290,6 +290,55 @@ def edt_cuda(labels, anisotropy=None, black_border=False, *, sqrt=False, signed=
     labels.data_ptr(), nbytes, nd, sx, sy, sz, wx, wy, wz, int(bool(black_border)), flags,
     out.data_ptr(), labels.device.index, ctypes.c_void_p(stream)))
   return out
+
+
+# ---------------------------------------------------------------------------------------
+# downstream helper of the reference's headline use case: one multi-label transform, then one
+# masked image per label (src/edt.pyx:951-994; README.md:23, 204)
+# ---------------------------------------------------------------------------------------
+
+def each(labels, dt, in_place=False):
+  """Iterator over (label, distance transform of that label alone), labels in ascending order,
+  background skipped -- same contract as the reference's edt.each (src/edt.pyx:951-994), which
+  builds it from run lists (src/edt_voxel_graph.hpp:238-310); here it is a masked copy per
+  label.  in_place=True reuses one read-only image between iterations, as the reference does."""
+  labels = np.asarray(labels)
+  dt = np.asarray(dt)
+  if labels.shape != dt.shape:
+    raise ValueError("labels and dt must have the same shape")
+  order = "F" if labels.flags.f_contiguous else "C"
+  keys = [k for k in np.unique(labels) if k != 0]
+
+  class ImageIterator:
+    def __len__(self):
+      return len(keys)
+
+    def __iter__(self):
+      img = np.zeros(labels.shape, dtype=np.float32, order=order) if in_place else None
+      for key in keys:
+        mask = labels == key
+        if in_place:
+          img.setflags(write=1)
+          img[...] = 0
+          img[mask] = dt[mask]
+          img.setflags(write=0)
+          yield (key, img)
+        else:
+          out = np.zeros(labels.shape, dtype=np.float32, order=order)
+          out[mask] = dt[mask]
+          yield (key, out)
+
+  return ImageIterator()
+
+
+def each_cuda(labels, dt):
+  """Device-resident `each`: yields (label, dt masked to that label) as torch CUDA tensors, so the
+  per-label images never cross PCIe."""
+  import torch
+  keys = [int(k) for k in torch.unique(labels).tolist() if k != 0]
+  zero = torch.zeros((), dtype=dt.dtype, device=dt.device)
+  for key in keys:
+    yield key, torch.where(labels == key, dt, zero)
 
 
 def release():

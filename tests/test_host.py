@@ -89,3 +89,25 @@ def test_label_views(edt):
   d = np.array([-0.0, 2.0], dtype=np.float64)
   assert edt._label_view(d)[0] == 0
   assert edt._label_view(np.zeros(3, np.float16)) is None
+
+
+def test_each_mirrors_reference_contract(edt):
+  """edt.each (src/edt.pyx:951-994, automated_test.py:831-856): per-label images from one
+  multi-label transform; pure host post-processing, so it is testable without a GPU."""
+  rng = np.random.default_rng(8)
+  labels = rng.integers(0, 6, (9, 8, 7)).astype(np.uint32)
+  dt = rng.random((9, 8, 7)).astype(np.float32) * (labels != 0)
+  for in_place in (False, True):
+    it = edt.each(labels, dt, in_place=in_place)
+    assert len(it) == len(set(np.unique(labels)) - {0})
+    seen = []
+    for label, img in it:
+      assert np.array_equal(img, (labels == label) * dt)
+      assert img.dtype == np.float32
+      if in_place:
+        assert not img.flags.writeable
+      seen.append(int(label))
+    assert seen == sorted(seen) and 0 not in seen
+  f = np.asfortranarray(labels)
+  _, img = next(iter(edt.each(f, np.asfortranarray(dt))))
+  assert img.flags.f_contiguous
