@@ -490,13 +490,23 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
   const int64_t lines = g.inner_count * g.outer_count;
   const size_t bytes = sizeof(float) * (size_t)lines * (size_t)g.n;
   float* tmp = nullptr;
+  int* hull = nullptr;
   CUDA_TRY(cudaMallocAsync(&tmp, bytes, stream));
+  if (cudaMallocAsync(&hull, bytes, stream) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFreeAsync(tmp, stream);
+    return fail(EDTB200_ENOMEM, "no device memory for the long-line scratch volumes");
+  }
   const int64_t blocks = (lines + 127) / 128;
-  if (blocks > 0x7fffffffLL) { cudaFreeAsync(tmp, stream); return fail(EDTB200_ELIMIT, "too many lines"); }
+  if (blocks > 0x7fffffffLL) {
+    cudaFreeAsync(tmp, stream); cudaFreeAsync(hull, stream);
+    return fail(EDTB200_ELIMIT, "too many lines");
+  }
   later_axis_long_kernel<Bytes><<<(unsigned)blocks, 128, 0, stream>>>(
-      static_cast<const LT*>(labels), f, tmp, g, w2, border_lo, border_hi, flags);
+      static_cast<const LT*>(labels), f, tmp, hull, g, w2, border_lo, border_hi, flags);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(f, tmp, bytes, cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(cudaFreeAsync(hull, stream));
   CUDA_TRY(cudaFreeAsync(tmp, stream));
   return 0;
 }

@@ -1110,10 +1110,9 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
 }
 
 // ---------------------------------------------------------------------------------------
-// Later-axis pass for lines too long for a shared-memory tile: one thread per line, lanes
-// on adjacent lines (coalesced), reading f_in / labels through L1/L2 and writing f_out
-// (out of place, so no tile-wide synchronisation is needed).  Same arithmetic; distances
-// of 4096 voxels and more, whose squares are not exact in float32, go through double.
+// Later-axis pass for lines too long for a shared-memory tile (more than 4096 voxels).  Same
+// arithmetic as the tile kernel; distances of 4096 voxels and more, whose squares are not exact
+// in float32, go through double (parabola_at).
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float parabola_at(float w2, int d, float height) {
   if (d < 4096) {
@@ -1124,10 +1123,15 @@ __device__ __forceinline__ float parabola_at(float w2, int d, float height) {
   return (float)__dadd_rn(__dmul_rn((double)w2, e * e), (double)height);
 }
 
+// One thread per line, lanes on adjacent lines (coalesced while the lanes stay in step).  Each
+// run of equal labels gets the classic lower-envelope scan (build the hull, then read it out),
+// O(n) per line, with the vertex stack in a global scratch volume `hull` laid out like f (entry
+// k of the run that starts at row a lives at row a + k of the same line) and everything read
+// through L1/L2.  Out of place (fin -> fout), so no synchronisation is needed.
 template <int Bytes>
 __global__ void __launch_bounds__(128)
 later_axis_long_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
-                       const float* __restrict__ fin, float* __restrict__ fout,
+                       const float* __restrict__ fin, float* __restrict__ fout, int* __restrict__ hull,
                        LineGeom g, float w2, int border_lo, int border_hi, int flags) {
   using LT = typename LabelOf<Bytes>::type;
   const int64_t lines_per_outer = g.inner_count;
@@ -1137,30 +1141,58 @@ later_axis_long_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
   const int64_t base = outer * g.outer_stride + (gid - outer * lines_per_outer);
   const int64_t ls = g.line_stride;
   const int n = g.n;
+  const float inf = __int_as_float(0x7f800000);
+  const double w2d = (double)w2;
 
-  int run_lo = 0;
-  int run_hi = 0;            // exclusive end of the current run; recomputed when i reaches it
-  LT mine = 0;
-  for (int i = 0; i < n; ++i) {
-    if (i == run_hi) {
-      run_lo = i;
-      mine = labels[base + (int64_t)i * ls];
-      int j = i + 1;
-      while (j < n && labels[base + (int64_t)j * ls] == mine) ++j;
-      run_hi = j;
+  int a = 0;
+  while (a < n) {
+    const LT mine = labels[base + (int64_t)a * ls];
+    int b = a + 1;
+    while (b < n && labels[base + (int64_t)b * ls] == mine) ++b;
+    const bool lo_border = a > 0 || border_lo;
+    const bool hi_border = b < n || border_hi;
+
+    // ---- build: hull[a + k] = position of the k-th vertex ----
+    int top = -1, q = 0, p = 0;
+    float fq = 0.0f, fp = 0.0f;
+    for (int r = a; r < b; ++r) {
+      const float fr = fin[base + (int64_t)r * ls];
+      if (!(fr < inf)) continue;                         // +inf: not a site
+      while (top >= 1 && vertex_hidden(p, fp, q, fq, r, fr, w2d)) {
+        --top;
+        q = p; fq = fp;
+        if (top >= 1) {
+          p = hull[base + (int64_t)(a + top - 1) * ls];
+          fp = fin[base + (int64_t)p * ls];
+        }
+      }
+      ++top;
+      hull[base + (int64_t)(a + top) * ls] = r;
+      p = q; fp = fq;
+      q = r; fq = fr;
     }
-    const int dl = i - run_lo;
-    const int dr = run_hi - 1 - i;
-    float best = fin[base + (int64_t)i * ls];
-    if (run_lo > 0 || border_lo) best = fminf(best, parabola_at(w2, dl + 1, 0.0f));
-    if (run_hi < n || border_hi) best = fminf(best, parabola_at(w2, dr + 1, 0.0f));
-    const int dmax = max(dl, dr);
-    for (int d = 1; d <= dmax; ++d) {
-      if (!(parabola_at(w2, d, 0.0f) < best)) break;
-      if (d <= dl) best = fminf(best, parabola_at(w2, d, fin[base + (int64_t)(i - d) * ls]));
-      if (d <= dr) best = fminf(best, parabola_at(w2, d, fin[base + (int64_t)(i + d) * ls]));
+
+    // ---- read out ----
+    int k = 0, v = 0, v1 = 0;
+    float fv = inf, fv1 = inf;
+    if (top >= 0) { v = hull[base + (int64_t)a * ls]; fv = fin[base + (int64_t)v * ls]; }
+    if (top >= 1) { v1 = hull[base + (int64_t)(a + 1) * ls]; fv1 = fin[base + (int64_t)v1 * ls]; }
+    for (int i = a; i < b; ++i) {
+      float best = inf;
+      if (top >= 0) {
+        best = parabola_at(w2, abs(i - v), fv);
+        while (k < top) {
+          const float cand = parabola_at(w2, abs(i - v1), fv1);
+          if (!(cand <= best)) break;
+          best = cand; ++k; v = v1; fv = fv1;
+          if (k < top) { v1 = hull[base + (int64_t)(a + k + 1) * ls]; fv1 = fin[base + (int64_t)v1 * ls]; }
+        }
+      }
+      if (lo_border) best = fminf(best, parabola_at(w2, i - a + 1, 0.0f));
+      if (hi_border) best = fminf(best, parabola_at(w2, b - i, 0.0f));
+      fout[base + (int64_t)i * ls] = finish_value(best, mine == 0, flags);
     }
-    fout[base + (int64_t)i * ls] = finish_value(best, mine == 0, flags);
+    a = b;
   }
 }
 

@@ -133,6 +133,10 @@ def test_long_axes(edt, oracle):
     lab.flat[5] = 0
     for bb in (False, True):
       assert_same(edt.edtsq(lab, black_border=bb), oracle.edtsq(lab, black_border=bb), (shape, bb))
+  # a big 2-D image whose lines (5000 and 4500 pixels) are longer than a shared-memory tile on the
+  # second axis, almost all foreground: the long-line kernel must stay O(n) per line
+  img = cases.random_volume(rng, (5000, 4500), "sparse_zero", np.uint8)
+  assert_same(edt.edt(img, anisotropy=(1.0, 2.0)), oracle.edt(img, anisotropy=(1.0, 2.0)), "5000x4500 sparse")
 
 
 def test_label_widths_and_float_labels(edt, oracle):
