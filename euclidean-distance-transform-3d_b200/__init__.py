@@ -76,8 +76,8 @@ def _lib():
   lib.edtb200_slab_face_fixup.restype = ci
   lib.edtb200_profile_passes.argtypes = [ci]
   lib.edtb200_profile_passes.restype = ci
-  lib.edtb200_last_pass_ms.argtypes = [vp]
-  lib.edtb200_last_pass_ms.restype = ci
+  lib.edtb200_pass_ms.argtypes = [ci, vp]
+  lib.edtb200_pass_ms.restype = ci
   lib.edtb200_release.restype = ci
   _LIB = lib
   return lib

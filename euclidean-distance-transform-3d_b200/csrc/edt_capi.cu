@@ -552,17 +552,29 @@ edtb200::LineGeom geom_for_axis(int axis, int64_t sx, int64_t sy, int64_t sz) {
   return g;
 }
 
-// Optional per-pass timing for bench.py: four events recorded around the three passes of the
-// most recent transform on this thread (see edtb200_profile_passes / edtb200_last_pass_ms).
+// Optional per-pass timing for bench.py: with profiling on, every transform of this thread records
+// four CUDA events (before / between / after its axis passes) into a ring, so a timed loop can be
+// analysed afterwards without any synchronisation inside it (edtb200_profile_passes /
+// edtb200_pass_ms).
+constexpr int kProfileRing = 256;
 thread_local bool g_profile = false;
-thread_local cudaEvent_t g_pass_events[4] = {nullptr, nullptr, nullptr, nullptr};
-thread_local int g_pass_count = 0;
+thread_local cudaEvent_t g_pass_events[kProfileRing][4];
+thread_local bool g_pass_events_init = false;
+thread_local int g_pass_marks[kProfileRing];       // highest mark index recorded in the slot
+thread_local long g_pass_seq = 0;                  // transforms profiled so far
 
 void mark_pass(int idx, cudaStream_t stream) {
   if (!g_profile) return;
-  if (!g_pass_events[idx] && cudaEventCreate(&g_pass_events[idx]) != cudaSuccess) { cudaGetLastError(); return; }
-  cudaEventRecord(g_pass_events[idx], stream);
-  g_pass_count = idx;
+  if (!g_pass_events_init) {
+    for (auto& slot : g_pass_events) for (auto& e : slot) e = nullptr;
+    g_pass_events_init = true;
+  }
+  if (idx == 0) ++g_pass_seq;
+  const int slot = (int)((g_pass_seq - 1) % kProfileRing);
+  cudaEvent_t& e = g_pass_events[slot][idx];
+  if (!e && cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaEventRecord(e, stream);
+  g_pass_marks[slot] = idx;
 }
 
 // All passes of one transform on device-resident buffers.
@@ -780,16 +792,20 @@ int edtb200_slab_face_fixup(const void* labels_dev, int label_bytes, int64_t sx,
 
 int edtb200_profile_passes(int enable) {
   g_profile = enable != 0;
+  if (enable) g_pass_seq = 0;
   return 0;
 }
 
-int edtb200_last_pass_ms(float* ms3) {
+int edtb200_pass_ms(int steps_back, float* ms3) {
   if (!ms3) return fail(EDTB200_EINVAL, "null pointer");
   ms3[0] = ms3[1] = ms3[2] = 0.0f;
-  for (int i = 0; i < g_pass_count && i < 3; ++i) {
-    if (!g_pass_events[i] || !g_pass_events[i + 1]) break;
-    CUDA_TRY(cudaEventSynchronize(g_pass_events[i + 1]));
-    CUDA_TRY(cudaEventElapsedTime(&ms3[i], g_pass_events[i], g_pass_events[i + 1]));
+  if (steps_back < 0 || steps_back >= kProfileRing || steps_back >= g_pass_seq)
+    return fail(EDTB200_EINVAL, "no profiled transform %d steps back", steps_back);
+  const int slot = (int)((g_pass_seq - 1 - steps_back) % kProfileRing);
+  for (int i = 0; i < g_pass_marks[slot] && i < 3; ++i) {
+    if (!g_pass_events[slot][i] || !g_pass_events[slot][i + 1]) break;
+    CUDA_TRY(cudaEventSynchronize(g_pass_events[slot][i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms3[i], g_pass_events[slot][i], g_pass_events[slot][i + 1]));
   }
   return 0;
 }

@@ -203,13 +203,29 @@ def make_peer_halo(device, sy, sx, label_dtype, halo=32, group=None):
     return None, "%s: %s" % (type(exc).__name__, exc)
 
 
+_AUTO_PEER = {}
+
+
+def _auto_peer_halo(labels_local, sy, sx, halo, group):
+  """Cached PeerHalo for this configuration, or None (all ranks agree on which)."""
+  if not labels_local.is_cuda:
+    return None
+  key = (id(group), labels_local.device.index, int(sy), int(sx), labels_local.element_size(), int(halo))
+  if key not in _AUTO_PEER:
+    ph, _ = make_peer_halo(labels_local.device, sy, sx, labels_local.dtype, halo, group)
+    ok = torch.tensor([1 if ph is not None else 0], device=labels_local.device)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    _AUTO_PEER[key] = ph if int(ok.item()) == 1 else None
+  return _AUTO_PEER[key]
+
+
 def _peer(group, r):
   return dist.get_global_rank(group, r) if group is not None else r
 
 
 def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False, *, sqrt=False,
                    signed=False, group=None, passes=None, halo=32, method="auto", info=None, depths=None,
-                   peer_halo=None, defer_check=False):
+                   peer_halo="auto", defer_check=False):
   """Distance transform of a volume distributed as Z slabs (axis 0) over the ranks of `group`.
 
   labels_local : this rank's slab, integer tensor (zc, sy, sx), C-contiguous; slabs are ordered by
@@ -220,7 +236,10 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   (raise if not exact), "transpose".  `info`, if a dict, receives {"method": ...}.
   depths: slab depth of every rank, if the caller knows them (saves one small all-reduce per call).
   peer_halo: a PeerHalo (symmetric-memory staging); the fix-up then reads the neighbours' faces
-  directly over NVLink instead of receiving `halo` planes through NCCL send/recv.
+  directly over NVLink instead of receiving `halo` planes through NCCL send/recv.  "auto" (the
+  default) creates and caches one per (group, plane shape, label width, halo) the first time CUDA
+  slabs are transformed -- a collective step, so every rank must make the same first call -- and
+  falls back to the NCCL exchange when symmetric memory is not available; None forces NCCL.
   defer_check: the halo method is taken optimistically and its exactness verdict (a device int,
   all-reduced) is normally read at the end of the call, which costs one host synchronisation.
   With defer_check=True the call returns without reading it and puts it in info["verdict"]
@@ -259,6 +278,8 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
 
   # ---- can the halo method be used?  decided on the labels alone, before any pass runs ----
   use_halo = method in ("auto", "halo") and world > 1 and min(depths) > halo
+  if isinstance(peer_halo, str):
+    peer_halo = _auto_peer_halo(labels_local, sy, sx, halo, group) if (use_halo and peer_halo == "auto") else None
   m_lo = m_hi = None
   if use_halo:
     overflow = torch.zeros(1, dtype=torch.int32, device=labels_local.device)

@@ -127,12 +127,13 @@ int edtb200_slab_face_fixup(const void *labels_dev, int label_bytes,
                             int flags, const void *nb_label_dev, const unsigned char *nb_m_dev,
                             const float *nb_f_dev, float *f_dev, int device, void *stream);
 
-/* Measurement hooks (used by bench.py): with profiling enabled on the calling thread,
- * edtb200_transform records CUDA events around its axis passes on the transform's stream;
- * edtb200_last_pass_ms waits for the last transform and returns the device time of the first,
- * second and third axis pass in milliseconds (0 for passes that did not run). */
+/* Measurement hooks (used by bench.py): with profiling enabled on the calling thread, every
+ * edtb200_transform records CUDA events around its axis passes on the transform's stream into a
+ * ring of 256 slots -- nothing synchronises inside a timed loop.  edtb200_pass_ms(k, ms) waits
+ * for the transform issued k calls ago (0 = the latest) and returns the device time of its
+ * first, second and third axis pass in milliseconds (0 for passes that did not run). */
 int edtb200_profile_passes(int enable);
-int edtb200_last_pass_ms(float *ms3);
+int edtb200_pass_ms(int steps_back, float *ms3);
 
 /* Free every cached device buffer / stream this library holds on all devices. */
 int edtb200_release(void);

@@ -252,7 +252,7 @@ def _nccl_worker(rank, world, port, queue):
         z0, zc = parts[rank]
         local = torch.from_numpy(vol[z0:z0 + zc].copy()).cuda()
         whole = edt_b200.edt_cuda(torch.from_numpy(vol).cuda(), an, bb, sqrt=sqrt, signed=signed)
-        for method, peer in (("auto", None), ("transpose", None), ("auto", peer_halo)):
+        for method, peer in (("auto", None), ("transpose", None), ("auto", peer_halo), ("auto", "auto")):
           if method == "auto" and peer is None and peer_halo is not None and False:
             continue
           info = {}
@@ -262,7 +262,7 @@ def _nccl_worker(rank, world, port, queue):
           want_method = expect if method == "auto" else "transpose"
           bad = int((out != whole[z0:z0 + zc]).sum().item())
           queue.put((rank, bad == 0 and info["method"] == want_method, bad, info["method"], want_method,
-                     "peer" if peer is not None else "nccl", peer_why))
+                     "nccl" if peer is None else "peer", peer_why))
   finally:
     dist.destroy_process_group()
 
@@ -277,7 +277,7 @@ def test_slab_split_nccl_two_gpus():
   procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, queue)) for r in range(2)]
   for p in procs:
     p.start()
-  results = [queue.get(timeout=300) for _ in range(24)]
+  results = [queue.get(timeout=300) for _ in range(32)]
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
