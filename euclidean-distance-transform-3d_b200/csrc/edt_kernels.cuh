@@ -898,6 +898,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       // hullw (bits relative to i0), and are stitched and read out in stages 2 and 3.
       uint32_t hb = 0u;
       uint32_t cflags = 0u;
+      bool has_long = false;
       const uint32_t todo = wstart & rowmask & ~single;
       int next_start = -1;                                 // first run start after this chunk (lazy)
       for (uint32_t rest = todo; rest;) {
@@ -946,6 +947,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
             hb = build_hull<TX>(ln, i0, sa, i0 + 32, w2d, hb);
           }
           crossing = 1;
+          has_long = true;
         }
       }
       // rows of a long run that entered from the chunk below (short ones were finished by their owner)
@@ -978,10 +980,11 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
             hb = build_hull<TX>(ln, i0, i0, seg_end, w2d, hb);
           }
           crossing = 1;
+          has_long = true;
         }
       }
       sts_u32(ln.hull + (uint32_t)c * ROW, hb);
-      sts_u8(cflagcol + (uint32_t)c * TX, cflags);
+      if (has_long) sts_u8(cflagcol + (uint32_t)c * TX, cflags);   // only ever read for chunks on long runs
     }
   }
   if (!__syncthreads_or(crossing)) return;                 // every run was finished inside its chunk
