@@ -17,7 +17,8 @@ Reference entry points mirrored here (file:line in the reference):
 Differences, all additive: ``parallel`` is accepted and ignored (the CUDA grid replaces the
 thread pool); keyword-only ``device=`` selects the GPU; ``sdf``/``sdfsq`` run ONE fused
 transform (background treated as a label, sign applied in the last store) instead of two;
-``voxel_graph`` is not implemented yet and raises ``NotImplementedError``.
+``voxel_graph=`` (2-D / 3-D, src/edt.pyx:514-620, 736-844) draws the doubled grid and runs
+the transform on the device.
 ``edt_cuda`` transforms a torch CUDA tensor without touching host memory.
 """
 import ctypes
@@ -36,6 +37,7 @@ FLAG_SQRT = 1
 FLAG_SIGNED = 2
 FLAG_LABELS_ON_DEVICE = 4
 FLAG_OUT_ON_DEVICE = 8
+FLAG_LABELS_FLOAT = 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
@@ -66,6 +68,8 @@ def _lib():
   lib.edtb200_device_count.restype = ci
   lib.edtb200_transform.argtypes = [vp, ci, ci, i64, i64, i64, f32, f32, f32, ci, ci, vp, ci, vp]
   lib.edtb200_transform.restype = ci
+  lib.edtb200_transform_voxel_graph.argtypes = [vp, ci, vp, ci, i64, i64, i64, f32, f32, f32, ci, ci, vp, ci, vp]
+  lib.edtb200_transform_voxel_graph.restype = ci
   lib.edtb200_pass_first.argtypes = [vp, ci, i64, i64, i64, f32, ci, ci, vp, ci, vp]
   lib.edtb200_pass_first.restype = ci
   lib.edtb200_pass_later.argtypes = [vp, ci, ci, i64, i64, i64, f32, ci, ci, ci, vp, ci, vp]
@@ -150,6 +154,38 @@ def _transform_host(data, anisotropy, black_border, flags, device):
   return out.reshape(data.shape, order=order)
 
 
+def _graph_bytes(voxel_graph, order):
+  """The graph as uint8 in the data's memory order (src/edt.pyx:294-298, 527-530)."""
+  g = np.asarray(voxel_graph)
+  g = np.ascontiguousarray(g) if order == "C" else np.asfortranarray(g)
+  return g.view(np.uint8) if g.dtype in (np.uint8, np.int8) else g.astype(np.uint8)
+
+
+def _transform_voxel_graph_host(data, voxel_graph, anisotropy, black_border, flags, device):
+  """__edt2dsq_voxel_graph / __edt3dsq_voxel_graph, src/edt.pyx:514-620, 736-844."""
+  order = "F" if data.flags.f_contiguous else "C"
+  if not data.flags.c_contiguous and not data.flags.f_contiguous:
+    data = np.ascontiguousarray(data)
+  graph = _graph_bytes(voxel_graph, order)
+  if graph.shape != data.shape:
+    raise ValueError("voxel_graph must have the shape of data")
+  dt = data.dtype
+  if dt == np.bool_:
+    labels = data.view(np.uint8)
+  elif dt.kind in "iu" and dt.itemsize in (1, 2, 4, 8):
+    labels = data.view(np.dtype("u%d" % dt.itemsize))
+  elif dt in (np.float32, np.float64):
+    labels, flags = data, flags | FLAG_LABELS_FLOAT
+  else:
+    return np.zeros(data.shape, dtype=np.float32, order=order)   # no branch in the reference either
+  (sx, sy, sz), (wx, wy, wz) = _x_fastest(data.shape, anisotropy, order == "F")
+  out = np.empty(data.size, dtype=np.float32)
+  _check(_lib().edtb200_transform_voxel_graph(
+    labels.ctypes.data, labels.dtype.itemsize, graph.ctypes.data, data.ndim, sx, sy, sz, wx, wy, wz,
+    int(bool(black_border)), int(flags), out.ctypes.data, int(device), None))
+  return out.reshape(data.shape, order=order)
+
+
 def _front_door(data, anisotropy, black_border, voxel_graph, flags, device, fixed_dims=None):
   """Argument handling of edtsq(), src/edt.pyx:276-310."""
   if isinstance(data, list):
@@ -163,7 +199,14 @@ def _front_door(data, anisotropy, black_border, voxel_graph, flags, device, fixe
   if voxel_graph is not None:
     if dims not in (2, 3):
       raise TypeError("Voxel connectivity graph is only supported for 2D and 3D. Got {}.".format(dims))
-    raise NotImplementedError("edt_b200: voxel_graph is not implemented on the GPU path yet")
+    anisotropy = nvl(anisotropy, (1.0,) * dims)
+    if flags & FLAG_SIGNED:
+      # sdf / sdfsq with a graph: f(data) - f(data == 0), both under the graph (src/edt.pyx:147-158)
+      dt = _transform_voxel_graph_host(data, voxel_graph, anisotropy, black_border, flags & ~FLAG_SIGNED, device)
+      dt -= _transform_voxel_graph_host(data == 0, voxel_graph, anisotropy, black_border, flags & ~FLAG_SIGNED,
+                                        device)
+      return dt
+    return _transform_voxel_graph_host(data, voxel_graph, anisotropy, black_border, flags, device)
   if dims == 1:
     anisotropy = nvl(anisotropy, 1.0)
     if np.ndim(anisotropy) != 0:
@@ -253,10 +296,13 @@ def _torch_label_bytes(torch):
   return _TORCH_LABEL_BYTES
 
 
-def edt_cuda(labels, anisotropy=None, black_border=False, *, sqrt=False, signed=False, out=None):
+def edt_cuda(labels, anisotropy=None, black_border=False, *, sqrt=False, signed=False, out=None,
+             voxel_graph=None):
   """Transform a C-contiguous integer/bool torch CUDA tensor of 1-3 dims on its own device
   and current stream, asynchronously; returns a float32 CUDA tensor of the same shape
-  (`out` may be passed to reuse a buffer).  Same semantics as edtsq/edt/sdfsq/sdf."""
+  (`out` may be passed to reuse a buffer).  Same semantics as edtsq/edt/sdfsq/sdf.
+  `voxel_graph` (a uint8/int8 CUDA tensor of the same shape, 2-D / 3-D only, not with `signed`)
+  selects the connectivity-graph transform."""
   import torch
   if not (isinstance(labels, torch.Tensor) and labels.is_cuda):
     raise TypeError("edt_cuda expects a torch CUDA tensor")
@@ -286,6 +332,19 @@ def edt_cuda(labels, anisotropy=None, black_border=False, *, sqrt=False, signed=
   if signed:
     flags |= FLAG_SIGNED
   stream = torch.cuda.current_stream(labels.device).cuda_stream
+  if voxel_graph is not None:
+    if nd not in (2, 3):
+      raise TypeError("Voxel connectivity graph is only supported for 2D and 3D. Got {}.".format(nd))
+    if signed:
+      raise ValueError("edt_cuda: with voxel_graph, form f(labels) - f(labels == 0) from two calls")
+    if not (isinstance(voxel_graph, torch.Tensor) and voxel_graph.device == labels.device
+            and voxel_graph.dtype in (torch.uint8, torch.int8) and voxel_graph.shape == labels.shape):
+      raise ValueError("edt_cuda: voxel_graph must be a uint8/int8 CUDA tensor shaped like labels")
+    voxel_graph = voxel_graph.contiguous()
+    _check(_lib().edtb200_transform_voxel_graph(
+      labels.data_ptr(), nbytes, voxel_graph.data_ptr(), nd, sx, sy, sz, wx, wy, wz,
+      int(bool(black_border)), flags, out.data_ptr(), labels.device.index, ctypes.c_void_p(stream)))
+    return out
   _check(_lib().edtb200_transform(
     labels.data_ptr(), nbytes, nd, sx, sy, sz, wx, wy, wz, int(bool(black_border)), flags,
     out.data_ptr(), labels.device.index, ctypes.c_void_p(stream)))

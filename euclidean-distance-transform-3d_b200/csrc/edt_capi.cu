@@ -6,6 +6,7 @@
 // passes are stream-ordered kernel launches.  No CPU fallback exists in this file.
 #include "../../include/edt_b200.h"
 #include "edt_kernels.cuh"
+#include "edt_voxel_graph.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -402,7 +403,7 @@ size_t tile_smem_bytes(int n, int tx, int rows_alloc) {
 
 template <int Bytes, int TX>
 int launch_tile(const void* labels, float* f, edtb200::LineGeom g, float w2, int border_lo, int border_hi,
-                int flags, bool use_tma, cudaStream_t stream, int code_bit = 0) {
+                int flags, bool use_tma, cudaStream_t stream, int code_bit = 0, bool pdl = false) {
   using namespace edtb200;
   using LT = typename LabelOf<Bytes>::type;
   const int nchunks = (g.n + 31) >> 5;
@@ -423,18 +424,29 @@ int launch_tile(const void* labels, float* f, edtb200::LineGeom g, float w2, int
   const bool wide = warps > 16;                 // long lines: one tile per SM, so give it 32 warps
   if (warps > 32) warps = 32;
   const LT* lab = static_cast<const LT*>(labels);
+  // Programmatic dependent launch: this pass may begin (label staging) while the previous pass of
+  // the stream drains its last wave; the kernel itself waits before touching the distances.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles);
+  cfg.blockDim = dim3((unsigned)(warps * 32));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = pdl_attr;
+  static const bool pdl_off = getenv("EDTB200_NO_PDL") != nullptr;    // A/B switch for measurements
+  cfg.numAttrs = (pdl && !pdl_off) ? 1 : 0;   // only when the previous kernel of the stream is our own pass
 #define EDT_LAUNCH_TILE(EPI, TMA, CODES)                                                            \
   do {                                                                                              \
     if (wide) {                                                                                     \
       auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, CODES, true>;                         \
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, lab, f, g, tb, w2, border_lo, border_hi, flags, \
-                                                          code_bit);                                \
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, lab, f, g, tb, w2, border_lo, border_hi, flags, code_bit)); \
     } else {                                                                                        \
       auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, CODES, false>;                        \
       CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      kern<<<(unsigned)tiles, warps * 32, smem, stream>>>(map, lab, f, g, tb, w2, border_lo, border_hi, flags, \
-                                                          code_bit);                                \
+      CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, lab, f, g, tb, w2, border_lo, border_hi, flags, code_bit)); \
     }                                                                                               \
   } while (0)
   if constexpr (Bytes == 1) {
@@ -456,7 +468,8 @@ int launch_tile(const void* labels, float* f, edtb200::LineGeom g, float w2, int
 // caller must have checked tile_path_ok() because only the tile kernel understands codes.
 template <int Bytes>
 int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, float w, int border_lo,
-                 int border_hi, int flags, const DeviceCache& dc, cudaStream_t stream, int code_bit = 0) {
+                 int border_hi, int flags, const DeviceCache& dc, cudaStream_t stream, int code_bit = 0,
+                 bool pdl = false) {
   using namespace edtb200;
   using LT = typename LabelOf<Bytes>::type;
   LineGeom g = g0;
@@ -479,9 +492,9 @@ int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, floa
     if (tx) {
       const bool use_tma = aligned && g.inner_count >= tx;
       switch (tx) {
-        case 32: return launch_tile<Bytes, 32>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit);
-        case 16: return launch_tile<Bytes, 16>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit);
-        default: return launch_tile<Bytes, 8>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit);
+        case 32: return launch_tile<Bytes, 32>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit, pdl);
+        case 16: return launch_tile<Bytes, 16>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit, pdl);
+        default: return launch_tile<Bytes, 8>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit, pdl);
       }
     }
   }
@@ -532,12 +545,13 @@ bool tile_path_ok(const edtb200::LineGeom& g, const DeviceCache& dc) {
 }
 
 int dispatch_later(int label_bytes, const void* labels, float* f, const edtb200::LineGeom& g, float w,
-                   int lo, int hi, int flags, const DeviceCache& dc, cudaStream_t s, int code_bit = 0) {
+                   int lo, int hi, int flags, const DeviceCache& dc, cudaStream_t s, int code_bit = 0,
+                   bool pdl = false) {
   switch (label_bytes) {
-    case 1: return launch_later<1>(labels, f, g, w, lo, hi, flags, dc, s, code_bit);
-    case 2: return launch_later<2>(labels, f, g, w, lo, hi, flags, dc, s);
-    case 4: return launch_later<4>(labels, f, g, w, lo, hi, flags, dc, s);
-    default: return launch_later<8>(labels, f, g, w, lo, hi, flags, dc, s);
+    case 1: return launch_later<1>(labels, f, g, w, lo, hi, flags, dc, s, code_bit, pdl);
+    case 2: return launch_later<2>(labels, f, g, w, lo, hi, flags, dc, s, code_bit, pdl);
+    case 4: return launch_later<4>(labels, f, g, w, lo, hi, flags, dc, s, code_bit, pdl);
+    default: return launch_later<8>(labels, f, g, w, lo, hi, flags, dc, s, code_bit, pdl);
   }
 }
 
@@ -592,6 +606,10 @@ int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_
   // voxel of HBM traffic).  Measured on B200, 512^3 uint32: Y 0.261 -> 0.244 ms, Z 0.280 -> 0.250 ms,
   // but the first-axis pass 0.180 -> 0.350 ms (two more label rows through L2 + 75 registers), a
   // net loss (0.84 vs 0.73 ms), so the passes read the labels by default.
+  // The later passes are launched with programmatic stream serialization: the kernel before them
+  // in the stream is our own previous pass, which never writes the labels, so their label staging
+  // (before griddepcontrol.wait) may overlap its tail.  The per-axis entry points do not do this:
+  // there the previous kernel is the caller's and may be the one producing the labels.
   int rc = 0;
   uint8_t* codes = nullptr;
   bool codes_done = false;
@@ -606,12 +624,13 @@ int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_
   if (!rc && ndim >= 2) {
     rc = codes_done ? dispatch_later(1, codes, f, gy, wy, border, border, ndim == 2 ? epilogue : 0, dc, stream, 1)
                     : dispatch_later(label_bytes, labels, f, gy, wy, border, border, ndim == 2 ? epilogue : 0, dc,
-                                     stream, 0);
+                                     stream, 0, /*pdl=*/true);
     mark_pass(2, stream);
   }
   if (!rc && ndim >= 3) {
     rc = codes_done ? dispatch_later(1, codes, f, gz, wz, border, border, epilogue, dc, stream, 2)
-                    : dispatch_later(label_bytes, labels, f, gz, wz, border, border, epilogue, dc, stream, 0);
+                    : dispatch_later(label_bytes, labels, f, gz, wz, border, border, epilogue, dc, stream, 0,
+                                     /*pdl=*/true);
     mark_pass(3, stream);
   }
   if (codes) cudaFreeAsync(codes, stream);
@@ -692,6 +711,96 @@ int edtb200_transform(const void* labels, int label_bytes, int ndim, int64_t sx,
     if (rc) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int edtb200_transform_voxel_graph(const void* labels, int label_bytes, const unsigned char* graph, int ndim,
+                                  int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                                  int black_border, int flags, float* out, int device, void* stream_v) {
+  using namespace edtb200;
+  if (ndim != 2 && ndim != 3)
+    return fail(EDTB200_EINVAL, "a voxel graph needs a 2-D or 3-D volume (got ndim %d)", ndim);
+  if (flags & EDTB200_SIGNED)
+    return fail(EDTB200_EINVAL, "EDTB200_SIGNED is not defined with a voxel graph: subtract two transforms");
+  if ((flags & EDTB200_LABELS_FLOAT) && label_bytes != 4 && label_bytes != 8)
+    return fail(EDTB200_EINVAL, "EDTB200_LABELS_FLOAT needs 4- or 8-byte labels");
+  int rc = check_dims(label_bytes, ndim, sx, sy, sz);
+  if (rc) return rc;
+  const int64_t total = sx * sy * sz;
+  if (total == 0) return 0;
+  if (!labels || !graph || !out) return fail(EDTB200_EINVAL, "null pointer");
+  int64_t sx2 = 2 * sx, sy2 = 2 * sy, sz2 = ndim == 3 ? 2 * sz : 1;
+  rc = check_dims(1, ndim, sx2, sy2, sz2);
+  if (rc) return rc;
+  const int64_t total2 = sx2 * sy2 * sz2;
+
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceGuard restore_device;
+  DeviceCache* dc = nullptr;
+  rc = probe(device, &dc);
+  if (rc) return rc;
+  const bool in_dev = flags & EDTB200_LABELS_ON_DEVICE;
+  const bool out_dev = flags & EDTB200_OUT_ON_DEVICE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!stream && !(in_dev && out_dev)) {
+    if (!dc->stream) CUDA_TRY(cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking));
+    stream = dc->stream;
+  }
+
+  // stream-ordered scratch: the inputs when they come from the host, the doubled byte mask, the
+  // doubled distance volume, and the result when it goes back to the host
+  void *d_labels = nullptr, *d_graph = nullptr, *d_cells = nullptr, *d_doubled = nullptr, *d_result = nullptr;
+  auto release = [&]() {
+    void* all[] = {d_labels, d_graph, d_cells, d_doubled, d_result};
+    for (void* p : all) if (p) cudaFreeAsync(p, stream);
+  };
+  #define VG_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { release(); \
+      return fail(e_ == cudaErrorMemoryAllocation ? EDTB200_ENOMEM : EDTB200_ECUDA, "%s: %s", #expr, \
+                  cudaGetErrorString(e_)); } } while (0)
+  const void* lab = labels;
+  const uint8_t* gr = graph;
+  if (!in_dev) {
+    VG_TRY(cudaMallocAsync(&d_labels, (size_t)total * label_bytes, stream));
+    VG_TRY(cudaMallocAsync(&d_graph, (size_t)total, stream));
+    rc = upload(d_labels, labels, (size_t)total * label_bytes, device, stream);
+    if (!rc) rc = upload(d_graph, graph, (size_t)total, device, stream);
+    if (rc) { release(); return rc; }
+    lab = d_labels;
+    gr = static_cast<const uint8_t*>(d_graph);
+  }
+  VG_TRY(cudaMallocAsync(&d_cells, (size_t)total2, stream));
+  VG_TRY(cudaMallocAsync(&d_doubled, (size_t)total2 * sizeof(float), stream));
+  float* result = out;
+  if (!out_dev) {
+    VG_TRY(cudaMallocAsync(&d_result, (size_t)total * sizeof(float), stream));
+    result = static_cast<float*>(d_result);
+  }
+
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, (int64_t)dc->sm_count * 32);
+  const int border = black_border != 0, as_float = (flags & EDTB200_LABELS_FLOAT) ? 1 : 0;
+  uint8_t* cells = static_cast<uint8_t*>(d_cells);
+  switch (label_bytes) {
+    case 1: voxel_graph_expand_kernel<1><<<blocks, threads, 0, stream>>>(lab, gr, cells, sx, sy, sz, ndim, border, as_float); break;
+    case 2: voxel_graph_expand_kernel<2><<<blocks, threads, 0, stream>>>(lab, gr, cells, sx, sy, sz, ndim, border, as_float); break;
+    case 4: voxel_graph_expand_kernel<4><<<blocks, threads, 0, stream>>>(lab, gr, cells, sx, sy, sz, ndim, border, as_float); break;
+    default: voxel_graph_expand_kernel<8><<<blocks, threads, 0, stream>>>(lab, gr, cells, sx, sy, sz, ndim, border, as_float); break;
+  }
+  VG_TRY(cudaGetLastError());
+  // half the anisotropy (vg:102-107, 199-204); the sqrt is taken by the gather instead
+  rc = run_passes(cells, 1, ndim, sx2, sy2, sz2, wx / 2, wy / 2, wz / 2, border, 0,
+                  static_cast<float*>(d_doubled), *dc, stream);
+  if (rc) { release(); return rc; }
+  voxel_graph_gather_kernel<<<blocks, threads, 0, stream>>>(static_cast<const float*>(d_doubled), result, sx, sy, sz,
+                                                            (flags & EDTB200_SQRT) ? 1 : 0);
+  VG_TRY(cudaGetLastError());
+  if (!out_dev) {
+    rc = download(out, result, (size_t)total * sizeof(float), device, stream);
+    if (rc) { release(); return rc; }
+  }
+  release();
+  if (!(in_dev && out_dev)) VG_TRY(cudaStreamSynchronize(stream));
+  #undef VG_TRY
   return 0;
 }
 

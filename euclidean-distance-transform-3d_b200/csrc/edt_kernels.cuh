@@ -37,6 +37,16 @@ template <> struct LabelOf<2> { using type = uint16_t; using wide = uint32_t; };
 template <> struct LabelOf<4> { using type = uint32_t; using wide = uint32_t; };
 template <> struct LabelOf<8> { using type = uint64_t; using wide = unsigned long long; };
 
+// Programmatic dependent launch (PDL): a kernel lets the next kernel of the stream start filling
+// the SM slots that free up during its last wave; the dependent kernel does whatever does not
+// touch the distance volume (staging the labels) and then waits for the whole grid before it.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_for_previous_grid() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ float finish_value(float v, bool background, int flags) {
   if (flags & kSqrt) v = __fsqrt_rn(v);                 // np.sqrt / std::sqrt: IEEE-correct
   if ((flags & kNegate) && background) v = -v;          // sdf: f(data) - f(data==0)
@@ -232,6 +242,7 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
   using LT = typename LabelOf<Bytes>::type;
   using WT = typename LabelOf<Bytes>::wide;
   extern __shared__ float table_s[];                 // T[0..sx], then +inf at sx + 1
+  pdl_launch_dependents();                           // the second-axis pass may start staging labels
   for (int i = threadIdx.x; i <= sx; i += blockDim.x) table_s[i] = __ldg(table + i);
   if (threadIdx.x == 0) table_s[sx + 1] = __int_as_float(0x7f800000);
   __syncthreads();
@@ -783,7 +794,10 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   const float inf = __int_as_float(0x7f800000);
   const double w2d = (double)w2;
 
+  pdl_launch_dependents();             // the next pass may start staging its labels during our tail
+  if (!UseTMA) pdl_wait_for_previous_grid();           // plain loads of f happen in the staging loop
   if (UseTMA && threadIdx.x == 0) {
+    pdl_wait_for_previous_grid();      // f is complete only when the previous pass has finished
     mbar_init(bar, 1);
     mbar_expect_tx(bar, (unsigned)rows_alloc * ROW);
     for (int bx = 0; bx < tb.nboxes; ++bx)
@@ -838,6 +852,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
     sts_u32(startw_a + (uint32_t)c * ROW + (uint32_t)x * 4u, wstart);
     if (Epilogue) sts_u32(zerow_a + (uint32_t)c * ROW + (uint32_t)x * 4u, wzero);
   }
+  pdl_wait_for_previous_grid();        // nobody may store into f before the previous pass is done
   __syncthreads();         // words, table (and plain-loaded tile) visible; orders the mbarrier init
   if (UseTMA) mbar_wait(bar, 0);       // float tile has landed
 

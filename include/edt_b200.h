@@ -40,6 +40,9 @@ extern "C" {
                                        (src/edt.pyx:121-202) */
 #define EDTB200_LABELS_ON_DEVICE 4  /* `labels` is a device pointer on `device` */
 #define EDTB200_OUT_ON_DEVICE    8  /* `out` is a device pointer on `device` */
+#define EDTB200_LABELS_FLOAT    16  /* edtb200_transform_voxel_graph only: the 4- / 8-byte labels are
+                                       IEEE floats and foreground means value > 0, as the reference's
+                                       float instantiations test it (src/edt_voxel_graph.hpp:76, 151) */
 
 /* error codes */
 #define EDTB200_EINVAL  (-1)   /* bad argument */
@@ -77,6 +80,28 @@ int edtb200_transform(const void *labels, int label_bytes, int ndim,
                       float wx, float wy, float wz,
                       int black_border, int flags,
                       float *out, int device, void *stream);
+
+/* Transform under a voxel connectivity graph (2-D or 3-D only).
+ *
+ * Replaces  pyedt::_edt2dsq_voxel_graph<T, uint8_t>   src/edt_voxel_graph.hpp:54-123
+ *           pyedt::_edt3dsq_voxel_graph<T, uint8_t>   src/edt_voxel_graph.hpp:125-214
+ *           pyedt::_edt3d_voxel_graph  (EDTB200_SQRT) src/edt_voxel_graph.hpp:216-236
+ * as bound by __edt2dsq_voxel_graph / __edt3dsq_voxel_graph, src/edt.pyx:514-620, 736-844.
+ *
+ *   graph   sx*sy*sz bytes, laid out like the labels; bit 0 / 2 / 4 set = the step to the +x / +y /
+ *           +z neighbour is allowed (the cc3d voxel-connectivity bit field; other bits are not read)
+ * Labels only say foreground (non-zero; > 0 with EDTB200_LABELS_FLOAT) or background here, as in
+ * the reference.  The foreground is drawn on a doubled grid in which a forbidden edge is a
+ * background cell, transformed with half the anisotropy, and sampled back; all of it on the device
+ * (scratch: 1 + 4 bytes per doubled cell).  EDTB200_LABELS_ON_DEVICE covers `labels` AND `graph`.
+ * EDTB200_SIGNED is rejected: the reference's sdf with a graph is the difference of two such
+ * transforms (src/edt.pyx:147-158), which the caller forms.
+ */
+int edtb200_transform_voxel_graph(const void *labels, int label_bytes, const unsigned char *graph,
+                                  int ndim, int64_t sx, int64_t sy, int64_t sz,
+                                  float wx, float wy, float wz,
+                                  int black_border, int flags,
+                                  float *out, int device, void *stream);
 
 /* Single axis passes on DEVICE-resident data, for callers that split a volume into Z slabs
  * across GPUs: every rank runs the first- and second-axis passes on

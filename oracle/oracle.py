@@ -131,27 +131,79 @@ def _run(fn, data, anisotropy, black_border):
   return out.reshape(data.shape, order=order)
 
 
+def voxel_graph_edtsq(data, voxel_graph, anisotropy=None, black_border=False):
+  """Restatement of _edt2dsq_voxel_graph / _edt3dsq_voxel_graph (edt_voxel_graph.hpp:54-214) as
+  bound by edt.pyx:514-620 and 736-844: draw the foreground (label > 0, labels not told apart)
+  on a grid of twice the resolution -- even cells are the voxels, the cell after a voxel along
+  +x / +y / +z is foreground only if graph bit 0 / 2 / 4 allows that step, the other cells of
+  the 2x2(x2) block are foreground, and with a black border the last cell layer of every axis is
+  background -- take the binary transform at half the anisotropy, keep the even cells."""
+  data = np.asarray(data)
+  nd = data.ndim
+  if nd not in (2, 3):
+    raise TypeError("Voxel connectivity graph is only supported for 2D and 3D. Got {}.".format(nd))
+  if data.size == 0:
+    return np.zeros(shape=data.shape, dtype=np.float32)
+  if not data.flags.c_contiguous and not data.flags.f_contiguous:
+    data = np.ascontiguousarray(data)
+  f_order = data.flags.f_contiguous
+  graph = np.asarray(voxel_graph)
+  graph = np.asfortranarray(graph) if f_order else np.ascontiguousarray(graph)
+  graph = graph.view(np.uint8) if graph.dtype in (np.uint8, np.int8) else graph.astype(np.uint8)
+  if anisotropy is None:
+    anisotropy = (1.0,) * nd
+  weights = [float(np.float32(a)) for a in anisotropy]
+  if data.dtype.kind == "f":
+    fg = data > 0
+  elif data.dtype == np.bool_:
+    fg = data
+  else:
+    fg = data != 0                       # astype(unsigned) > 0
+  # index the arrays as [x, y(, z)] with x the memory-fastest axis (edt.pyx:429-440, 651-664)
+  if not f_order:
+    fg, graph, weights = fg.T, graph.T, weights[::-1]
+  cells = np.zeros(tuple(2 * s for s in fg.shape), dtype=np.uint8, order="F")
+  even, odd = slice(0, None, 2), slice(1, None, 2)
+  edge_bits = (0x01, 0x04, 0x10)
+  for offs in np.ndindex(*(2,) * nd):
+    value = fg
+    if sum(offs) == 1:                   # the edge cell towards the next voxel of one axis
+      value = fg & ((graph & edge_bits[offs.index(1)]) != 0)
+    cells[tuple(odd if o else even for o in offs)] = value
+  if black_border:
+    for axis in range(nd):
+      last = [slice(None)] * nd
+      last[axis] = -1
+      cells[tuple(last)] = 0
+  doubled = edtsq(cells, tuple(w / 2 for w in weights), black_border)
+  out = np.asfortranarray(doubled[(even,) * nd])
+  return out if f_order else np.ascontiguousarray(out.T)
+
+
 def edtsq(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=None, order=None):
+  if voxel_graph is not None:
+    return voxel_graph_edtsq(data, voxel_graph, anisotropy, black_border)
   return _run(_lib().oracle_edtsq, data, anisotropy, black_border)
 
 
 def edt(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=None, order=None):
-  dt = edtsq(data, anisotropy, black_border)
+  dt = edtsq(data, anisotropy, black_border, voxel_graph=voxel_graph)
   return np.sqrt(dt, dt)
 
 
 def sdf(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=None, order=None):
   """edt.pyx:121-158: edt(data) - edt(data == 0)."""
   data = np.asarray(data)
-  dt = edt(data, anisotropy, black_border)
-  dt -= edt(data == 0, anisotropy, black_border)
+  dt = edt(data, anisotropy, black_border, voxel_graph=voxel_graph)
+  dt -= edt(data == 0, anisotropy, black_border, voxel_graph=voxel_graph)
   return dt
 
 
 def sdfsq(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=None):
   """edt.pyx:161-202."""
   data = np.asarray(data)
-  return edtsq(data, anisotropy, black_border) - edtsq(data == 0, anisotropy, black_border)
+  return (edtsq(data, anisotropy, black_border, voxel_graph=voxel_graph)
+          - edtsq(data == 0, anisotropy, black_border, voxel_graph=voxel_graph))
 
 
 def bruteforce_edtsq(data, anisotropy=None, black_border=False):

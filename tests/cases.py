@@ -169,3 +169,34 @@ def random_case(seed):
   an = ANISOTROPIES[(seed // 5) % len(ANISOTROPIES)][:nd]
   kwargs = dict(anisotropy=an[0] if nd == 1 else an, black_border=bool((seed // 2) % 2))
   return labels, kwargs
+
+
+def random_graph_case(seed):
+  """Deterministic (labels, graph, kwargs) for the voxel_graph path: 2-D / 3-D, every dtype, both
+  memory orders, graph bytes from 'everything allowed' to random bit fields of several dtypes."""
+  rng = np.random.default_rng(7000 + seed)
+  nd = 2 + seed % 2
+  hi = {2: 60, 3: 24}[nd]
+  shape = tuple(int(rng.integers(1, hi)) for _ in range(nd))
+  dtypes = [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16, np.int32, np.int64,
+            bool, np.float32, np.float64]
+  dtype = dtypes[(seed // 2) % len(dtypes)]
+  density = [0.97, 0.8, 1.0][seed % 3]
+  mask = rng.random(shape) < density
+  if dtype is bool:
+    labels = mask
+  elif np.dtype(dtype).kind == "f":
+    labels = (rng.integers(-1, 4, shape) * mask).astype(dtype)     # negatives are background here
+  else:
+    labels = (rng.integers(1, 5, shape) * mask).astype(dtype)
+  gdtype = [np.uint8, np.int8, np.uint32][(seed // 3) % 3]
+  graph = rng.integers(0, 64, shape)
+  allow_all = rng.random(shape) < [0.9, 0.5, 0.0][(seed // 4) % 3]
+  graph = np.where(allow_all, 63, graph).astype(gdtype)
+  if (seed // 3) % 2:
+    labels = np.asfortranarray(labels)
+  if (seed // 5) % 2:
+    graph = np.asfortranarray(graph)
+  an = ANISOTROPIES[(seed // 5) % len(ANISOTROPIES)][:nd]
+  kwargs = dict(anisotropy=an, black_border=bool((seed // 2) % 2))
+  return labels, graph, kwargs

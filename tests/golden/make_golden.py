@@ -3,7 +3,8 @@
 
 Run here (where /root/reference exists):  python tests/golden/make_golden.py
 The .npz is committed; the GPU box has no reference, so tests only read the fixture.
-Each case stores the input labels, the call arguments and the reference's edtsq / edt / sdf.
+Each case stores the input labels, the call arguments and the reference's edtsq / edt / sdf;
+the g* cases do the same for the voxel_graph= path.
 """
 import os
 import sys
@@ -19,6 +20,7 @@ import cases  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 SEEDS = list(range(1000, 1048))
+GRAPH_SEEDS = list(range(0, 36))
 
 
 def main():
@@ -42,6 +44,19 @@ def main():
   cfg1 = np.ones((64, 64, 64), dtype=np.uint32, order="F")
   blob["cfg1_edtsq"] = ref.edtsq(cfg1, black_border=True, parallel=1)
   blob["seeds"] = np.array(meta)
+  # voxel_graph path (edt.pyx:514-620, 736-844): edtsq / edt / sdf under a connectivity graph
+  for seed in GRAPH_SEEDS:
+    labels, graph, kwargs = cases.random_graph_case(seed)
+    key = "g%d" % seed
+    blob[key + "_labels"] = labels
+    blob[key + "_graph"] = graph
+    blob[key + "_aniso"] = np.asarray(kwargs["anisotropy"], dtype=np.float64)
+    blob[key + "_border"] = np.array(kwargs["black_border"])
+    with np.errstate(invalid="ignore"):
+      blob[key + "_edtsq"] = ref.edtsq(labels, voxel_graph=graph, **kwargs)
+      blob[key + "_edt"] = ref.edt(labels, voxel_graph=graph, **kwargs)
+      blob[key + "_sdf"] = ref.sdf(labels, voxel_graph=graph, **kwargs)
+  blob["graph_seeds"] = np.array(GRAPH_SEEDS)
   out = os.path.join(HERE, "reference_vectors.npz")
   np.savez_compressed(out, **blob)
   print("wrote", out, os.path.getsize(out), "bytes,", len(meta), "cases")

@@ -62,8 +62,8 @@ def test_front_door_mirrors_reference(edt):
     edt.edtsq(np.zeros((2, 2, 2, 2), np.uint8))       # src/edt.pyx:310
   with pytest.raises(TypeError):
     edt.edtsq(np.zeros((4,), np.uint8), voxel_graph=np.zeros((4,), np.uint8))   # src/edt.pyx:291-292
-  with pytest.raises(NotImplementedError):
-    edt.edtsq(np.zeros((4, 4), np.uint8), voxel_graph=np.zeros((4, 4), np.uint8))
+  with pytest.raises(ValueError):
+    edt.edtsq(np.zeros((4, 4), np.uint8), voxel_graph=np.zeros((4, 5), np.uint8))
 
 
 def test_axis_mapping(edt):

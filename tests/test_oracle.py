@@ -53,6 +53,39 @@ def test_golden_fixtures(oracle):
   assert got.max() == 1024.0
 
 
+def test_golden_voxel_graph_fixtures(oracle):
+  """The voxel_graph restatement (oracle.voxel_graph_edtsq) against the compiled reference's
+  outputs for edtsq / edt / sdf under a connectivity graph (edt.pyx:514-620, 736-844)."""
+  z = np.load(GOLDEN)
+  for seed in z["graph_seeds"]:
+    key = "g%d" % seed
+    labels, graph = z[key + "_labels"], z[key + "_graph"]
+    kw = dict(anisotropy=tuple(z[key + "_aniso"]), black_border=bool(z[key + "_border"]), voxel_graph=graph)
+    with np.errstate(invalid="ignore"):
+      assert same(oracle.edtsq(labels, **kw), z[key + "_edtsq"]), seed
+      assert same(oracle.edt(labels, **kw), z[key + "_edt"]), seed
+      assert same(oracle.sdf(labels, **kw), z[key + "_sdf"]), seed
+    l2, g2, k2 = cases.random_graph_case(int(seed))
+    assert np.array_equal(l2, labels) and np.array_equal(g2, graph)
+
+
+def test_voxel_graph_known_answer(oracle):
+  """The reference's own voxel-graph test, automated_test.py:736-789 (its first two asserts; the
+  third one there is vacuous, so the blocked-edge geometry is pinned by the fixtures instead)."""
+  labels = np.ones((5, 6), dtype=np.int64)
+  graph = np.full((5, 6), 0b111111, dtype=np.uint8)
+  assert np.all(oracle.edt(labels, voxel_graph=graph) == np.inf)
+  ring = np.array([[0.5] * 6, [0.5, 1.5, 1.5, 1.5, 1.5, 0.5], [0.5, 1.5, 2.5, 2.5, 1.5, 0.5],
+                   [0.5, 1.5, 1.5, 1.5, 1.5, 0.5], [0.5] * 6], dtype=np.float32)
+  assert same(oracle.edt(labels, voxel_graph=graph, black_border=True), ring)
+  # forbid the step between the two centre voxels of row 2: both end up half a voxel from background
+  graph[2, 2] = 0b111110
+  got = oracle.edt(labels, voxel_graph=graph, black_border=True)
+  assert got[2, 2] == 0.5 and got[2, 1] == 1.5 and got[1, 2] == np.float32(np.sqrt(1.25))
+  with pytest.raises(TypeError):
+    oracle.edtsq(np.ones(5, np.uint8), voxel_graph=np.ones(5, np.uint8))
+
+
 def test_fixture_cases_are_reproducible():
   """The generator is deterministic: the committed inputs equal cases.random_case(seed)."""
   z = np.load(GOLDEN)
@@ -71,6 +104,13 @@ def test_live_against_compiled_reference(oracle, reference):
     if seed % 3 == 0:
       assert same(oracle.sdf(labels, **kwargs), reference.sdf(labels, **kwargs)), seed
       assert same(oracle.edt(labels, **kwargs), reference.edt(labels, **kwargs)), seed
+  for seed in range(100, 160):
+    labels, graph, kwargs = cases.random_graph_case(seed)
+    with np.errstate(invalid="ignore"):
+      assert same(oracle.edtsq(labels, voxel_graph=graph, **kwargs),
+                  reference.edtsq(labels, voxel_graph=graph, **kwargs)), seed
+      assert same(oracle.sdf(labels, voxel_graph=graph, **kwargs),
+                  reference.sdf(labels, voxel_graph=graph, **kwargs)), seed
 
 
 def test_definition_bruteforce(oracle):

@@ -82,6 +82,57 @@ def test_golden_fixtures(edt):
   assert got.max() == 1024.0 and got.flags.f_contiguous
 
 
+# ---- voxel_graph= path (src/edt_voxel_graph.hpp:54-236, edt.pyx:514-620, 736-844) --------------
+
+def test_voxel_graph_golden_fixtures(edt):
+  z = np.load(GOLDEN)
+  for seed in z["graph_seeds"]:
+    key = "g%d" % seed
+    labels, graph = z[key + "_labels"], z[key + "_graph"]
+    kw = dict(anisotropy=tuple(z[key + "_aniso"]), black_border=bool(z[key + "_border"]), voxel_graph=graph)
+    got = edt.edtsq(labels, **kw)
+    assert_same(got, z[key + "_edtsq"], ("edtsq", seed))
+    assert got.flags.f_contiguous == z[key + "_edtsq"].flags.f_contiguous
+    with np.errstate(invalid="ignore"):
+      assert ulp_diff(edt.edt(labels, **kw), z[key + "_edt"]) <= 1, seed
+      assert ulp_diff(edt.sdf(labels, **kw), z[key + "_sdf"]) <= 1, seed
+
+
+def test_voxel_graph_known_answer_and_random(edt, oracle):
+  labels = np.ones((5, 6), dtype=np.int64)                       # automated_test.py:736-789
+  graph = np.full((5, 6), 0b111111, dtype=np.uint8)
+  assert np.all(edt.edt(labels, voxel_graph=graph) == np.inf)
+  ring = np.array([[0.5] * 6, [0.5, 1.5, 1.5, 1.5, 1.5, 0.5], [0.5, 1.5, 2.5, 2.5, 1.5, 0.5],
+                   [0.5, 1.5, 1.5, 1.5, 1.5, 0.5], [0.5] * 6], dtype=np.float32)
+  assert_same(edt.edt(labels, voxel_graph=graph, black_border=True), ring, "ring")
+  graph[2, 2], graph[2, 3] = 0b111110, 0b111101
+  for g in (graph, np.asfortranarray(graph)):
+    assert_same(edt.edt(labels, voxel_graph=g, black_border=True),
+                oracle.edt(labels, voxel_graph=g, black_border=True), "blocked edge")
+  for seed in range(200, 260):
+    labels, graph, kwargs = cases.random_graph_case(seed)
+    what = (seed, labels.shape, labels.dtype.name, kwargs)
+    assert_same(edt.edtsq(labels, voxel_graph=graph, **kwargs),
+                oracle.edtsq(labels, voxel_graph=graph, **kwargs), ("edtsq",) + what)
+    if seed % 4 == 0:
+      with np.errstate(invalid="ignore"):
+        assert_same(edt.sdfsq(labels, voxel_graph=graph, **kwargs),
+                    oracle.sdfsq(labels, voxel_graph=graph, **kwargs), ("sdfsq",) + what)
+  # a volume large enough for the tile kernels on the doubled grid (2 * 96 = 192 rows per axis)
+  rng = np.random.default_rng(11)
+  labels = (rng.random((96, 80, 72)) < 0.995).astype(np.uint16)
+  graph = np.where(rng.random(labels.shape) < 0.98, 63, rng.integers(0, 64, labels.shape)).astype(np.uint8)
+  assert_same(edt.edt(labels, anisotropy=(4, 4, 40), black_border=True, voxel_graph=graph),
+              oracle.edt(labels, anisotropy=(4, 4, 40), black_border=True, voxel_graph=graph), "96x80x72")
+  with pytest.raises(TypeError):
+    edt.edtsq(np.ones(5, np.uint8), voxel_graph=np.ones(5, np.uint8))
+  import torch                                                       # device-resident entry
+  got = edt.edt_cuda(torch.from_numpy(labels.astype(np.int16)).cuda(), (4, 4, 40), True, sqrt=True,
+                     voxel_graph=torch.from_numpy(graph).cuda())
+  assert_same(got.cpu().numpy(), oracle.edt(labels, anisotropy=(4, 4, 40), black_border=True, voxel_graph=graph),
+              "edt_cuda voxel_graph")
+
+
 # ---- randomized differential tests against the oracle -----------------------------------
 
 @pytest.mark.parametrize("block", range(8))
