@@ -142,7 +142,12 @@ CopyPool* g_pool = nullptr;           // created on first use, under g_mutex
 void parallel_memcpy(void* dst, const void* src, size_t bytes) {
   if (!g_pool) {
     unsigned hw = std::thread::hardware_concurrency();
-    g_pool = new CopyPool(hw >= 16 ? 8 : (hw >= 4 ? 4 : 1));
+    // measured on the B200 host (2 x 64 threads), 512 MiB each way: 8 threads 40 ms, 16 threads
+    // 31 ms, 32 threads 38 ms per numpy-to-numpy call; populating the fresh output array's pages
+    // from helper threads during the upload was tried and only made it slower (44-68 ms)
+    int n = hw >= 32 ? 16 : (hw >= 16 ? 8 : (hw >= 4 ? 4 : 1));
+    if (const char* e = getenv("EDTB200_COPY_THREADS")) n = std::max(1, std::min(64, atoi(e)));
+    g_pool = new CopyPool(n);
   }
   const int n = g_pool->size();
   const size_t slice = ((bytes + n - 1) / n + 4095) & ~size_t(4095);
