@@ -76,7 +76,7 @@ def _lib():
   lib.edtb200_pass_later.restype = ci
   lib.edtb200_slab_face_runs.argtypes = [vp, ci, i64, i64, i64, ci, ci, ci, vp, vp, ci, vp]
   lib.edtb200_slab_face_runs.restype = ci
-  lib.edtb200_slab_face_fixup.argtypes = [vp, ci, i64, i64, i64, ci, ci, f32, ci, vp, vp, vp, vp, ci, vp]
+  lib.edtb200_slab_face_fixup.argtypes = [vp, ci, i64, i64, i64, ci, ci, f32, ci, vp, vp, vp, vp, vp, ci, vp]
   lib.edtb200_slab_face_fixup.restype = ci
   lib.edtb200_profile_passes.argtypes = [ci]
   lib.edtb200_profile_passes.restype = ci

@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda.h>          // CUtensorMap (type only; the encoder is fetched at run time)
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 namespace edtb200 {
@@ -1254,12 +1255,20 @@ face_runs_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, int64
 //   nb_label : the neighbour's face plane of labels        nb_m : its face_runs_kernel output
 //   nb_f     : H planes of the neighbour's distances AFTER its second-axis pass, in the
 //              neighbour's own z order (for the low face these are its LAST H planes)
+// When the neighbour's part of the run is longer than the halo (nb_m = H + 1) its first H rows
+// are still folded in, and the sites behind them -- unseen, at distance >= j + 1 + H from row j,
+// so never cheaper than w2 * (j + 1 + H)^2 -- are ruled out by VALUE: if the combined result of a
+// row does not exceed that bound nothing unseen can beat it.  sqrt of the result is 1-Lipschitz
+// along the run (in units of w), so the bound holding at the face row implies it for every deeper
+// row; it is tested (with one row of slack against rounding) on every row the walk visits, and
+// *inexact is raised when it fails -- the caller then needs a deeper halo or the exact fallback.
 template <int Bytes>
 __global__ void __launch_bounds__(256)
 face_fixup_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, float* __restrict__ f,
                   int64_t plane, int nz, int high_face, int H, float w2,
                   const typename LabelOf<Bytes>::type* __restrict__ nb_label,
-                  const uint8_t* __restrict__ nb_m, const float* __restrict__ nb_f, int flags) {
+                  const uint8_t* __restrict__ nb_m, const float* __restrict__ nb_f, int flags,
+                  int* __restrict__ inexact) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= plane) return;
   const int64_t row0 = high_face ? (int64_t)(nz - 1) : 0;
@@ -1268,22 +1277,28 @@ face_fixup_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, floa
   const bool background = lab0 == 0;
   if (background && !(flags & kZeroLabel)) return;            // plain EDT: background stays 0
   const bool same = nb_label[q] == lab0;
-  const int m = same ? min((int)nb_m[q], H) : 0;              // neighbour rows of this run (<= H; H + 1 means
-                                                              // "too long": the caller discards this result)
+  const int m_raw = same ? (int)nb_m[q] : 0;
+  const bool unseen = m_raw > H;                              // the run goes on behind the halo
+  const int m = min(m_raw, H);                                // neighbour rows of this run that we hold
   const bool negative = (flags & kNegate) && background;
   for (int j = 0; j < nz; ++j) {
     const int64_t at = (row0 + step * j) * plane + q;
     if (j > 0 && labels[at] != lab0) break;                   // end of the run inside this slab
-    // best outside site for row j: neighbour rows r = 0..m-1 at distance j + 1 + r, then the
-    // zero-height site behind them at distance j + 1 + m
-    float best = parabola_at(w2, j + 1 + m, 0.0f);
+    // best outside site for row j: neighbour rows r = 0..m-1 at distance j + 1 + r, then (if the
+    // run ends there) the zero-height site behind them at distance j + 1 + m
+    float best = unseen ? CUDART_INF_F : parabola_at(w2, j + 1 + m, 0.0f);
     for (int r = 0; r < m; ++r) {
       const int64_t src = (high_face ? (int64_t)r : (int64_t)(H - 1 - r)) * plane + q;
       best = fminf(best, parabola_at(w2, j + 1 + r, nb_f[src]));
     }
     if (flags & kSqrt) best = __fsqrt_rn(best);
-    const float cur = f[at];
-    if (!(best < fabsf(cur))) break;                          // no outside site helps from here on
+    const float cur = fabsf(f[at]);
+    if (unseen) {
+      float bound = parabola_at(w2, j + H, 0.0f);
+      if (flags & kSqrt) bound = __fsqrt_rn(bound);
+      if (!(fminf(best, cur) <= bound) && inexact) *inexact = 1;
+    }
+    if (!(best < cur)) break;                                 // no outside site helps from here on
     f[at] = negative ? -best : best;
   }
 }

@@ -12,9 +12,11 @@ split along the slowest axis into contiguous slabs, one per rank.
     faces open, while ONE neighbour exchange ships, per face, the face plane of labels, the
     length of the face-touching run of every (x,y) line and the last/first `halo` planes of the
     Y-pass distances (34 MiB per face at 512 x 512, halo 32).  `edtb200_slab_face_fixup` then
-    folds the neighbour's sites into the face-touching runs.  Exact as long as no foreground
-    run reaches deeper than `halo` rows into a neighbouring slab; that is checked on the labels
-    before anything else runs (one int all-reduce), otherwise:
+    folds the neighbour's sites into the face-touching runs.  Exact when every face-crossing run
+    ends within `halo` rows of the face on the far side, OR goes on but the distances at the
+    face do not exceed the halo's reach (value <= (w_z * halo)^2: a site behind the halo is then
+    too far away to win).  The fix-up kernel checks the second condition on the values it
+    produces and raises a device flag (one int all-reduce after the step), otherwise:
   * Method "transpose" (exact for any input): one all-to-all turns the Z-slab layout into a
     Y-slab layout (every rank then owns complete z-lines for a range of y), the ordinary Z-pass
     kernel runs with the volume's real border flags, and a second all-to-all brings the result
@@ -95,14 +97,16 @@ class CudaPasses:
                                                 overflow.data_ptr(), self.device.index, self._stream()))
     return m
 
-  def face_fixup(self, labels, f, high_face, halo, wz, sqrt, signed, nb_label, nb_m, nb_f):
+  def face_fixup(self, labels, f, high_face, halo, wz, sqrt, signed, nb_label, nb_m, nb_f, inexact):
+    """`inexact` (device int32[1]) is raised when a run continues behind the halo AND the distances
+    at the face are larger than the halo reaches, i.e. an unseen site could still win."""
     sz, sy, sx = labels.shape
     nbytes = _torch_label_bytes(torch)[labels.dtype]
     flags = (FLAG_SQRT if sqrt else 0) | (FLAG_SIGNED if signed else 0)
     self._check(self.lib.edtb200_slab_face_fixup(labels.data_ptr(), nbytes, sx, sy, sz, int(high_face),
                                                  int(halo), float(wz), flags, nb_label.data_ptr(),
                                                  nb_m.data_ptr(), nb_f.data_ptr(), f.data_ptr(),
-                                                 self.device.index, self._stream()))
+                                                 inexact.data_ptr(), self.device.index, self._stream()))
 
 
 def _all_to_all(send_chunks, recv_chunks, group):
@@ -232,16 +236,17 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
                  rank and every rank passes the same sy, sx (zc may differ, 0 is allowed).
   Returns this rank's slab of the result (float32, same shape).  Semantics of edtsq (default),
   edt (sqrt=True), sdfsq (signed=True) and sdf (both) of the reference, on the WHOLE volume.
-  method: "auto" (halo exchange when it is exact for these labels, else transpose), "halo"
-  (raise if not exact), "transpose".  `info`, if a dict, receives {"method": ...}.
+  method: "auto" (halo exchange, repeated with transpose when its verdict says it was not exact
+  for this volume), "halo" (raise if not exact), "transpose".  `info`, if a dict, receives {"method": ...}.
   depths: slab depth of every rank, if the caller knows them (saves one small all-reduce per call).
   peer_halo: a PeerHalo (symmetric-memory staging); the fix-up then reads the neighbours' faces
   directly over NVLink instead of receiving `halo` planes through NCCL send/recv.  "auto" (the
   default) creates and caches one per (group, plane shape, label width, halo) the first time CUDA
   slabs are transformed -- a collective step, so every rank must make the same first call -- and
   falls back to the NCCL exchange when symmetric memory is not available; None forces NCCL.
-  defer_check: the halo method is taken optimistically and its exactness verdict (a device int,
-  all-reduced) is normally read at the end of the call, which costs one host synchronisation.
+  defer_check: the halo method is taken optimistically and its exactness verdict (a device int
+  raised by the fix-up kernels, all-reduced) is normally read at the end of the call, which costs
+  one host synchronisation.
   With defer_check=True the call returns without reading it and puts it in info["verdict"]
   (call `check_verdicts` on a batch of them later); a non-zero verdict means the result must be
   recomputed with method="transpose".
@@ -276,13 +281,14 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
       raise ValueError("depths must list the slab depth of every rank")
   sz = sum(depths)
 
-  # ---- can the halo method be used?  decided on the labels alone, before any pass runs ----
+  # ---- the halo method is taken optimistically; its verdict comes from the fix-up kernels ----
   use_halo = method in ("auto", "halo") and world > 1 and min(depths) > halo
   if isinstance(peer_halo, str):
     peer_halo = _auto_peer_halo(labels_local, sy, sx, halo, group) if (use_halo and peer_halo == "auto") else None
   m_lo = m_hi = None
   if use_halo:
-    overflow = torch.zeros(1, dtype=torch.int32, device=labels_local.device)
+    overflow = torch.zeros(1, dtype=torch.int32, device=labels_local.device)    # hint only, not reduced
+    inexact = torch.zeros(1, dtype=torch.int32, device=labels_local.device)
     stage = None
     if peer_halo is not None:
       if not peer_halo.matches(sy, sx, labels_local.dtype, halo):
@@ -294,9 +300,24 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
       m_lo = passes.face_runs(labels_local, 0, halo, signed, overflow, out=stage["m_lo"] if stage else None)
     if rank < world - 1:
       m_hi = passes.face_runs(labels_local, 1, halo, signed, overflow, out=stage["m_hi"] if stage else None)
-    # asynchronous: the compute stream must not wait for this tiny collective
-    overflow_work = dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=group, async_op=True)
-  mark("face_runs+allreduce")
+  mark("face_runs")
+
+  def halo_verdict(result):
+    """All-reduce the fix-up kernels' flag; hand it to the caller (deferred) or act on it."""
+    work = dist.all_reduce(inexact, op=dist.ReduceOp.MAX, group=group, async_op=True)
+    if defer_check:
+      if info is None:
+        raise ValueError("defer_check=True needs an `info` dict to receive the verdict")
+      info["verdict"] = (inexact, work)
+      return result
+    work.wait()
+    if int(inexact.item()) == 0:
+      return result
+    if method == "halo":
+      raise EDTError("halo method is not exact here: a run goes on behind the %d halo rows of a neighbouring "
+                     "slab and the distances at that face exceed the halo's reach" % halo)
+    return slab_transform(labels_local, anisotropy, black_border, sqrt=sqrt, signed=signed, group=group,
+                          passes=passes, halo=halo, method="transpose", info=info, depths=depths)
 
   # ---- X and Y passes: slab-local, no communication ----
   f = passes.empty_f32((zc, sy, sx))
@@ -337,25 +358,13 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     if rank > 0:
       nbv = peer_halo.views(rank - 1, parity)
       passes.face_fixup(labels_local, f, 0, halo, wz, sqrt, signed, nbv["lab_hi"].view(labels_local.dtype),
-                        nbv["m_hi"], nbv["f_hi"])
+                        nbv["m_hi"], nbv["f_hi"], inexact)
     if rank < world - 1:
       nbv = peer_halo.views(rank + 1, parity)
       passes.face_fixup(labels_local, f, 1, halo, wz, sqrt, signed, nbv["lab_lo"].view(labels_local.dtype),
-                        nbv["m_lo"], nbv["f_lo"])
+                        nbv["m_lo"], nbv["f_lo"], inexact)
     mark("face fix-up (peer reads)")
-    if defer_check:
-      if info is None:
-        raise ValueError("defer_check=True needs an `info` dict to receive the verdict")
-      info["verdict"] = (overflow, overflow_work)
-      return f
-    overflow_work.wait()
-    if int(overflow.item()) == 0:
-      return f
-    if method == "halo":
-      raise EDTError("halo method is not exact here: a run reaches deeper than %d rows into a "
-                     "neighbouring slab" % halo)
-    return slab_transform(labels_local, anisotropy, black_border, sqrt=sqrt, signed=signed, group=group,
-                          passes=passes, halo=halo, method="transpose", info=info, depths=depths)
+    return halo_verdict(f)
 
   if use_halo:
     # ---- one neighbour exchange: face labels, face run lengths, `halo` planes of distances ----
@@ -389,23 +398,9 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     mark("exchange done")
     for high_face, (r_label, r_m, r_f) in recv.items():
       nb_label = r_label.view(labels_local.dtype).reshape(sy, sx)
-      passes.face_fixup(labels_local, f, high_face, halo, wz, sqrt, signed, nb_label, r_m, r_f)
+      passes.face_fixup(labels_local, f, high_face, halo, wz, sqrt, signed, nb_label, r_m, r_f, inexact)
     mark("face fix-up")
-    # The halo path was taken optimistically so that the host never waits in the middle of a
-    # step; only now, with everything queued, is the (all-reduced) verdict of face_runs read.
-    if defer_check:
-      if info is None:
-        raise ValueError("defer_check=True needs an `info` dict to receive the verdict")
-      info["verdict"] = (overflow, overflow_work)
-      return f
-    overflow_work.wait()
-    if int(overflow.item()) == 0:
-      return f
-    if method == "halo":
-      raise EDTError("halo method is not exact here: a run reaches deeper than %d rows into a "
-                     "neighbouring slab" % halo)
-    return slab_transform(labels_local, anisotropy, black_border, sqrt=sqrt, signed=signed, group=group,
-                          passes=passes, halo=halo, method="transpose", info=info, depths=depths)
+    return halo_verdict(f)
 
   # ---- Z pass: Z slabs -> Y slabs (all-to-all), pass, back ----
   ysplit = split_extent(sy, world)

@@ -133,15 +133,18 @@ int edtb200_pass_later(const void *labels_dev, int label_bytes, int axis,
  *
  * edtb200_slab_face_runs : for every (x,y) line, the length m (1..halo) of the run of equal
  *     labels that touches the low (high_face=0) or high (high_face=1) face of this slab;
- *     m = halo+1 means "longer than the halo, or spanning the whole slab", and *overflow_dev
- *     (device int, zeroed by the caller) is raised when that happens for a foreground run
- *     (any run with EDTB200_SIGNED) -- the caller must then use an exact fallback.
+ *     m = halo+1 means "longer than the halo, or spanning the whole slab".  *overflow_dev (device
+ *     int, zeroed by the caller) is raised when that happens for a foreground run (any run with
+ *     EDTB200_SIGNED): a hint that the fix-up's verdict below matters for this volume.
  * edtb200_slab_face_fixup : after the third-axis pass (same flags: EDTB200_SQRT / SIGNED),
  *     min-combines every row of the face-touching runs with the neighbour's sites:
  *     nb_label_dev = the neighbour's face plane of labels, nb_m_dev = its face_runs output,
  *     nb_f_dev = `halo` planes of the neighbour's distances taken after ITS second-axis pass,
  *     in the neighbour's z order (its last `halo` planes for our low face, its first for our
- *     high face).  Requires sz > halo on both sides.
+ *     high face).  Requires sz > halo on both sides.  Runs that go on behind the halo are exact
+ *     as long as the distances at the face stay within the halo's reach (value <= (w*halo)^2);
+ *     *inexact_dev (device int, zeroed by the caller, may be NULL) is raised when they do not,
+ *     and the caller must then repeat with a deeper halo or an exact method.
  */
 int edtb200_slab_face_runs(const void *labels_dev, int label_bytes,
                            int64_t sx, int64_t sy, int64_t sz, int high_face, int halo, int flags,
@@ -150,7 +153,8 @@ int edtb200_slab_face_runs(const void *labels_dev, int label_bytes,
 int edtb200_slab_face_fixup(const void *labels_dev, int label_bytes,
                             int64_t sx, int64_t sy, int64_t sz, int high_face, int halo, float wz,
                             int flags, const void *nb_label_dev, const unsigned char *nb_m_dev,
-                            const float *nb_f_dev, float *f_dev, int device, void *stream);
+                            const float *nb_f_dev, float *f_dev, int *inexact_dev,
+                            int device, void *stream);
 
 /* Measurement hooks (used by bench.py): with profiling enabled on the calling thread, every
  * edtb200_transform records CUDA events around its axis passes on the transform's stream into a

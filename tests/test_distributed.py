@@ -70,7 +70,7 @@ class OraclePasses:
       overflow[0] = 1
     return torch.from_numpy(m.astype(np.uint8))
 
-  def face_fixup(self, labels, f, high_face, halo, wz, sqrt, signed, nb_label, nb_m, nb_f):
+  def face_fixup(self, labels, f, high_face, halo, wz, sqrt, signed, nb_label, nb_m, nb_f, inexact):
     lab, arr = labels.numpy(), f.numpy()
     nbl, nbm, nbf = nb_label.numpy(), nb_m.numpy(), nb_f.numpy()
     nz, sy, sx = lab.shape
@@ -81,19 +81,27 @@ class OraclePasses:
         lab0 = lab[row0, y, x]
         if lab0 == 0 and not signed:
           continue
-        m = min(int(nbm[y, x]), halo) if nbl[y, x] == lab0 else 0
+        m_raw = int(nbm[y, x]) if nbl[y, x] == lab0 else 0
+        unseen = m_raw > halo           # the neighbour's part of the run goes on behind the halo
+        m = min(m_raw, halo)
         for j in range(nz):
           r = row0 + step * j
           if j > 0 and lab[r, y, x] != lab0:
             break
-          best = np.float32(np.float64(w2) * (j + 1 + m) ** 2)
+          best = np.float32(np.inf) if unseen else np.float32(np.float64(w2) * (j + 1 + m) ** 2)
           for k in range(m):
             src = k if high_face else halo - 1 - k
             best = min(best, np.float32(np.float64(w2) * (j + 1 + k) ** 2 + np.float64(nbf[src, y, x])))
           if sqrt:
             best = np.sqrt(np.float32(best))
-          cur = arr[r, y, x]
-          if not (best < abs(cur)):
+          cur = abs(arr[r, y, x])
+          if unseen:
+            bound = np.float32(np.float64(w2) * (j + halo) ** 2)
+            if sqrt:
+              bound = np.sqrt(bound)
+            if not (min(best, cur) <= bound):
+              inexact[0] = 1
+          if not (best < cur):
             break
           arr[r, y, x] = -best if (signed and lab0 == 0) else best
 
@@ -112,6 +120,8 @@ def _volume(case):
   elif kind == "ones":
     vol = np.ones(shape, dtype=np.int64)
     vol[tuple(s // 2 for s in shape)] = 0
+  elif kind == "solid":
+    vol = np.full(shape, 7, dtype=np.int64)
   elif kind == "stripes":       # z-runs of length 2 starting at odd z (slab faces cut them), some background
     z, y, x = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
     vol = 1 + ((z + 1) // 2 + x + 2 * y) % 3
@@ -171,7 +181,14 @@ CASES = [
   ((12, 5, 6), "stripes", (1.0, 1.0, 1.0), False, False, False, None),    # halo method applies
   ((12, 5, 6), "stripes", (2.0, 3.0, 1.0), True, True, True, None),
   ((13, 4, 5), "stripes", (0.7, 1.0, 1.3), False, True, False, None),
+  # runs far longer than the halo (2 rows): still exact through the halo when the distances at the
+  # faces stay within its reach (w_z = 3: reach 6 >= the <= 3 voxels to the x / y borders) ...
+  ((16, 5, 7), "solid", (3.0, 1.0, 1.0), True, False, False, None),
+  ((16, 5, 7), "solid", (3.0, 1.0, 1.0), True, True, True, None),
+  # ... and not when they do not (w_z = 1: reach 2 < 3): the verdict sends it to the transpose
+  ((16, 5, 7), "solid", (1.0, 1.0, 1.0), True, False, False, None),
 ]
+EXPECT_HALO2 = {10: "halo", 11: "halo", 12: "transpose"}     # method taken with halo=2
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -211,6 +228,8 @@ def test_slab_split_matches_single_volume(world):
       assert len(methods) == 1, (world, idx, halo, methods)       # every rank took the same path
       if halo == 64:
         assert methods == {"transpose"}
+      elif idx in EXPECT_HALO2:
+        assert methods == {EXPECT_HALO2[idx]}, (world, idx, methods)
       used.add((idx, methods.pop()))
       assert np.array_equal(got, want, equal_nan=True), (world, idx, halo)
   assert any(m == "halo" for _, m in used) and any(m == "transpose" for _, m in used), used
@@ -243,10 +262,15 @@ def _nccl_worker(rank, world, port, queue):
     z, y, x = np.meshgrid(np.arange(143), np.arange(54), np.arange(70), indexing="ij")
     vol_a = (1 + ((z // 4) + (y // 9) * 3 + (x // 10) * 7) % 5).astype(np.int32)
     vol_a[60:90, 10:30, 5:50] = rng.integers(0, 3, (30, 20, 45))
-    # (b) big blocks: some runs are longer than the halo, "auto" must fall back
+    # (b) big blocks: runs longer than the halo (48 planes), but no voxel is further than 32 w_z from
+    # its region's boundary (the plane is 54 x 70), so the halo's reach check passes
     small = rng.integers(0, 2, (3, 6, 7))
     vol_b = np.repeat(np.repeat(np.repeat(small, 48, 0), 9, 1), 10, 2).astype(np.int32)[:143]
-    for vol, expect in ((vol_a, "halo"), (vol_b, "transpose")):
+    # (c) one label, one background voxel in a corner: the distances at the slab face (~70) are
+    # beyond the halo's reach, "auto" must notice and fall back
+    vol_c = np.full((143, 54, 70), 3, dtype=np.int32)
+    vol_c[0, 0, 0] = 0
+    for vol, expect in ((vol_a, "halo"), (vol_b, "halo"), (vol_c, "transpose")):
       for (bb, sqrt, signed, an) in ((False, False, False, (1.0, 1.0, 1.0)), (True, True, True, (3.0, 1.0, 2.0))):
         parts = ed.split_extent(vol.shape[0], world)
         z0, zc = parts[rank]
@@ -277,7 +301,7 @@ def test_slab_split_nccl_two_gpus():
   procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, queue)) for r in range(2)]
   for p in procs:
     p.start()
-  results = [queue.get(timeout=300) for _ in range(32)]
+  results = [queue.get(timeout=300) for _ in range(48)]
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
