@@ -270,8 +270,10 @@ def _nccl_worker(rank, world, port, queue):
     # beyond the halo's reach, "auto" must notice and fall back
     vol_c = np.full((143, 54, 70), 3, dtype=np.int32)
     vol_c[0, 0, 0] = 0
-    for vol, expect in ((vol_a, "halo"), (vol_b, "halo"), (vol_c, "transpose")):
-      for (bb, sqrt, signed, an) in ((False, False, False, (1.0, 1.0, 1.0)), (True, True, True, (3.0, 1.0, 2.0))):
+    # with the black border and w_z = 3 even (c) is within reach: nothing is further than 27 from a y border
+    for vol, expects in ((vol_a, ("halo", "halo")), (vol_b, ("halo", "halo")), (vol_c, ("transpose", "halo"))):
+      for expect, (bb, sqrt, signed, an) in zip(expects, ((False, False, False, (1.0, 1.0, 1.0)),
+                                                          (True, True, True, (3.0, 1.0, 2.0)))):
         parts = ed.split_extent(vol.shape[0], world)
         z0, zc = parts[rank]
         local = torch.from_numpy(vol[z0:z0 + zc].copy()).cuda()
@@ -305,4 +307,4 @@ def test_slab_split_nccl_two_gpus():
   for p in procs:
     p.join(timeout=60)
     assert p.exitcode == 0
-  assert all(r[1] for r in results), results
+  assert all(r[1] for r in results), [r for r in results if not r[1]]
