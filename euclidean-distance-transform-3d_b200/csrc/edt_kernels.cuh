@@ -1281,18 +1281,35 @@ face_fixup_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, floa
   const bool unseen = m_raw > H;                              // the run goes on behind the halo
   const int m = min(m_raw, H);                                // neighbour rows of this run that we hold
   const bool negative = (flags & kNegate) && background;
+  // the neighbour's rows of this run, read ONCE (they may live in a peer GPU's memory): every row
+  // of the walk below needs them again.  Only those within reach of the face row's value are
+  // fetched: deeper rows of this slab reach no further into the neighbour (Lipschitz again).
+  constexpr int kSiteCap = 128;
+  float sites[kSiteCap];
+  int held = 0;
+  {
+    const float cur0 = fabsf(f[row0 * plane + q]);
+    const float reach0 = (flags & kSqrt) ? cur0 * cur0 * 1.000001f : cur0;
+    while (held < min(m, kSiteCap) && parabola_at(w2, 1 + held, 0.0f) < reach0) {
+      sites[held] = nb_f[(high_face ? (int64_t)held : (int64_t)(H - 1 - held)) * plane + q];
+      ++held;
+    }
+  }
   for (int j = 0; j < nz; ++j) {
     const int64_t at = (row0 + step * j) * plane + q;
     if (j > 0 && labels[at] != lab0) break;                   // end of the run inside this slab
+    const float cur = fabsf(f[at]);
+    // a site at distance d costs at least w2 * d^2: beyond the current value's reach nothing helps
+    const float reach = (flags & kSqrt) ? cur * cur * 1.000001f : cur;
     // best outside site for row j: neighbour rows r = 0..m-1 at distance j + 1 + r, then (if the
     // run ends there) the zero-height site behind them at distance j + 1 + m
     float best = unseen ? CUDART_INF_F : parabola_at(w2, j + 1 + m, 0.0f);
     for (int r = 0; r < m; ++r) {
-      const int64_t src = (high_face ? (int64_t)r : (int64_t)(H - 1 - r)) * plane + q;
-      best = fminf(best, parabola_at(w2, j + 1 + r, nb_f[src]));
+      if (parabola_at(w2, j + 1 + r, 0.0f) >= reach) break;
+      const float height = r < held ? sites[r] : nb_f[(high_face ? (int64_t)r : (int64_t)(H - 1 - r)) * plane + q];
+      best = fminf(best, parabola_at(w2, j + 1 + r, height));
     }
     if (flags & kSqrt) best = __fsqrt_rn(best);
-    const float cur = fabsf(f[at]);
     if (unseen) {
       float bound = parabola_at(w2, j + H, 0.0f);
       if (flags & kSqrt) bound = __fsqrt_rn(bound);

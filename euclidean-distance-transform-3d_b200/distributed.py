@@ -227,8 +227,11 @@ def _peer(group, r):
   return dist.get_global_rank(group, r) if group is not None else r
 
 
+_HALO_HINT = {}      # (group, plane shape) -> halo depth that was last needed there
+
+
 def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False, *, sqrt=False,
-                   signed=False, group=None, passes=None, halo=32, method="auto", info=None, depths=None,
+                   signed=False, group=None, passes=None, halo=None, method="auto", info=None, depths=None,
                    peer_halo="auto", defer_check=False):
   """Distance transform of a volume distributed as Z slabs (axis 0) over the ranks of `group`.
 
@@ -236,8 +239,11 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
                  rank and every rank passes the same sy, sx (zc may differ, 0 is allowed).
   Returns this rank's slab of the result (float32, same shape).  Semantics of edtsq (default),
   edt (sqrt=True), sdfsq (signed=True) and sdf (both) of the reference, on the WHOLE volume.
-  method: "auto" (halo exchange, repeated with transpose when its verdict says it was not exact
-  for this volume), "halo" (raise if not exact), "transpose".  `info`, if a dict, receives {"method": ...}.
+  method: "auto" (halo exchange; when its verdict says it was not exact for this volume the step
+  is repeated with a four times deeper halo, up to 128 rows, then with transpose), "halo" (raise if
+  not exact), "transpose".
+  halo: rows of the neighbours' distances a rank can see (1..254).  None = 32, or the depth the
+  last "auto" call on the same group and plane shape ended up needing.  `info`, if a dict, receives {"method": ...}.
   depths: slab depth of every rank, if the caller knows them (saves one small all-reduce per call).
   peer_halo: a PeerHalo (symmetric-memory staging); the fix-up then reads the neighbours' faces
   directly over NVLink instead of receiving `halo` planes through NCCL send/recv.  "auto" (the
@@ -255,6 +261,11 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   rank = dist.get_rank(group)
   if passes is None:
     passes = CudaPasses(labels_local.device)
+  peer_halo_arg = peer_halo
+  hint_key = (id(group), tuple(labels_local.shape[1:]))
+  remember = halo is None and method == "auto"
+  if halo is None:
+    halo = _HALO_HINT.get(hint_key, 32) if method == "auto" else 32
   marks = info.get("marks") if isinstance(info, dict) else None      # optional CUDA-event phase marks
 
   def mark(name):
@@ -312,12 +323,25 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
       return result
     work.wait()
     if int(inexact.item()) == 0:
+      if info is not None:
+        info["halo"] = halo
+      if remember:
+        _HALO_HINT[hint_key] = halo
       return result
     if method == "halo":
       raise EDTError("halo method is not exact here: a run goes on behind the %d halo rows of a neighbouring "
                      "slab and the distances at that face exceed the halo's reach" % halo)
-    return slab_transform(labels_local, anisotropy, black_border, sqrt=sqrt, signed=signed, group=group,
-                          passes=passes, halo=halo, method="transpose", info=info, depths=depths)
+    deeper = min(4 * halo, 128)
+    sub = info if info is not None else {}
+    again = dict(sqrt=sqrt, signed=signed, group=group, passes=passes, info=sub, depths=depths)
+    if deeper > halo and min(depths) > deeper:
+      out = slab_transform(labels_local, anisotropy, black_border, halo=deeper, method="auto",
+                           peer_halo=None if peer_halo_arg is None else "auto", **again)
+    else:
+      out = slab_transform(labels_local, anisotropy, black_border, halo=halo, method="transpose", **again)
+    if remember and sub.get("method") == "halo":
+      _HALO_HINT[hint_key] = sub["halo"]
+    return out
 
   # ---- X and Y passes: slab-local, no communication ----
   f = passes.empty_f32((zc, sy, sx))

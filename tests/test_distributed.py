@@ -187,8 +187,12 @@ CASES = [
   ((16, 5, 7), "solid", (3.0, 1.0, 1.0), True, True, True, None),
   # ... and not when they do not (w_z = 1: reach 2 < 3): the verdict sends it to the transpose
   ((16, 5, 7), "solid", (1.0, 1.0, 1.0), True, False, False, None),
+  # ... unless the slabs are deep enough for the next halo depth (2 -> 8 rows: world 2 has 10-row slabs)
+  ((20, 5, 7), "solid", (1.0, 1.0, 1.0), True, False, False, None),
 ]
-EXPECT_HALO2 = {10: "halo", 11: "halo", 12: "transpose"}     # method taken with halo=2
+# method taken when starting with halo=2, per world size
+EXPECT_HALO2 = {10: {2: "halo", 3: "halo"}, 11: {2: "halo", 3: "halo"}, 12: {2: "transpose", 3: "transpose"},
+                13: {2: "halo", 3: "transpose"}}
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -229,7 +233,7 @@ def test_slab_split_matches_single_volume(world):
       if halo == 64:
         assert methods == {"transpose"}
       elif idx in EXPECT_HALO2:
-        assert methods == {EXPECT_HALO2[idx]}, (world, idx, methods)
+        assert methods == {EXPECT_HALO2[idx][world]}, (world, idx, methods)
       used.add((idx, methods.pop()))
       assert np.array_equal(got, want, equal_nan=True), (world, idx, halo)
   assert any(m == "halo" for _, m in used) and any(m == "transpose" for _, m in used), used

@@ -77,7 +77,7 @@ for name, make in WORKLOADS:
   flag = torch.tensor([1 if same else 0], device=dev)
   dist.all_reduce(flag, op=dist.ReduceOp.MIN)
   if rank == 0:
-    print("%-26s auto -> %-9s %7.2f ms/step (verdict read every step)   transpose %7.2f ms   equal to transpose: %s   max %.1f"
-          % (name, info["method"], auto_ms, tr_ms, bool(flag.item()), float(exact[torch.isfinite(exact)].max())), flush=True)
+    print("%-26s auto -> %-9s (halo %3s) %7.2f ms/step (verdict read every step)   transpose %7.2f ms   equal to transpose: %s   max %.1f"
+          % (name, info["method"], info.get("halo", "-"), auto_ms, tr_ms, bool(flag.item()), float(exact[torch.isfinite(exact)].max())), flush=True)
   del lab, exact, got
 dist.destroy_process_group()
