@@ -404,6 +404,56 @@ int main(int argc, char** argv) {
   assert np.array_equal(out[1], oracle.edt(lab, anisotropy=(2, 3, 5), black_border=False).ravel(order="F"))
 
 
+def test_cpp_voxel_graph_shim(edt, oracle, tmp_path):
+  """include/edt_voxel_graph.hpp: pyedt::_edt3dsq_voxel_graph / _edt2dsq_voxel_graph with the
+  reference's signatures (src/edt_voxel_graph.hpp:54-236), compiled with g++."""
+  import shutil
+  import subprocess
+  if shutil.which("g++") is None:
+    pytest.skip("no g++")
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  src = tmp_path / "vg.cpp"
+  src.write_text(r'''
+#include "edt_voxel_graph.hpp"
+#include <cstdio>
+#include <vector>
+int main(int argc, char** argv) {
+  const int sx = 13, sy = 9, sz = 6;
+  std::vector<float> lab(sx * sy * sz);
+  std::vector<uint8_t> graph(lab.size());
+  FILE* fi = fopen(argv[1], "rb");
+  if (!fi || fread(lab.data(), 4, lab.size(), fi) != lab.size()) return 2;
+  if (fread(graph.data(), 1, graph.size(), fi) != graph.size()) return 2;
+  fclose(fi);
+  float* a = pyedt::_edt3dsq_voxel_graph<float, uint8_t>(lab.data(), graph.data(), sx, sy, sz, 2.f, 3.f, 5.f, true);
+  float* b = pyedt::_edt3d_voxel_graph<float>(lab.data(), graph.data(), sx, sy, sz, 2.f, 3.f, 5.f, true);
+  std::vector<float> c(sx * sy);
+  float* cret = pyedt::_edt2dsq_voxel_graph<float>(lab.data(), graph.data(), sx, sy, 1.f, 1.f, false, c.data());
+  if (cret != c.data()) return 3;
+  FILE* fo = fopen(argv[2], "wb");
+  fwrite(a, 4, lab.size(), fo); fwrite(b, 4, lab.size(), fo); fwrite(c.data(), 4, c.size(), fo); fclose(fo);
+  delete[] a; delete[] b;
+  return 0;
+}
+''')
+  exe = tmp_path / "vg"
+  libdir = os.path.dirname(edt.library_path())
+  subprocess.run(["g++", "-std=c++17", "-I", os.path.join(root, "include"), str(src), "-L", libdir,
+                  "-ledt_b200", "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+  rng = np.random.default_rng(23)
+  lab = np.asfortranarray((rng.integers(-1, 3, (13, 9, 6)) * (rng.random((13, 9, 6)) < 0.9)).astype(np.float32))
+  graph = np.asfortranarray(np.where(rng.random(lab.shape) < 0.7, 63, rng.integers(0, 64, lab.shape)).astype(np.uint8))
+  (tmp_path / "in.bin").write_bytes(lab.tobytes(order="F") + graph.tobytes(order="F"))
+  subprocess.run([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], check=True)
+  out = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
+  n = lab.size
+  sq = oracle.edtsq(lab, anisotropy=(2, 3, 5), black_border=True, voxel_graph=graph)
+  assert np.array_equal(out[:n], sq.ravel(order="F"))
+  assert np.array_equal(out[n:2 * n], np.sqrt(sq).ravel(order="F"))
+  plane = oracle.edtsq(lab[:, :, 0], anisotropy=(1, 1), black_border=False, voxel_graph=graph[:, :, 0])
+  assert np.array_equal(out[2 * n:], plane.ravel(order="F"), equal_nan=True)
+
+
 def test_cfg4_1024_device_resident(edt):
   """BASELINE.json configs[3] size (1024^3), entirely on the device (8 GiB resident): closed
   form for the all-foreground box, and label-permutation / power-of-two scaling invariance for
@@ -431,6 +481,35 @@ def test_cfg4_1024_device_resident(edt):
   assert bool((edt.edt_cuda(relabelled) == base).all())
   del relabelled
   assert bool((edt.edt_cuda(lab, (4.0, 4.0, 4.0)) == base * 16.0).all())
+
+
+def test_more_than_2_31_voxels(edt):
+  """528 x 2048 x 2048 = 2.2e9 voxels (64-bit voxel indices everywhere), device-resident, against
+  closed forms: isolated boxes of edge 48 (long runs: chunk hulls + stitching) and 16 (short runs),
+  anisotropic, black border; labels of neighbouring boxes always differ."""
+  import torch
+  dev = torch.device("cuda", 0)
+  shape = (528, 2048, 2048)
+  w = (3.0, 1.0, 2.0)
+
+  def axis_terms(n, edge, weight):
+    i = torch.arange(n, device=dev, dtype=torch.int64)
+    p = i % edge
+    length = torch.minimum(torch.full_like(i, edge), n - (i - p))      # the last box may be cut by the volume
+    d = torch.minimum(p + 1, length - p).to(torch.float32)
+    return (weight * d) ** 2, (i // edge)
+
+  for edge in (48, 16):
+    (tz, bz), (ty, by), (tx, bx) = (axis_terms(n, edge, wt) for n, wt in zip(shape, w))
+    lab = (1 + (bz.view(-1, 1, 1) + 2 * by.view(1, -1, 1) + 4 * bx.view(1, 1, -1)) % 8).to(torch.uint8)
+    assert lab.numel() > 2**31
+    got = edt.edt_cuda(lab, w, True)
+    del lab
+    want = torch.minimum(torch.minimum(tz.view(-1, 1, 1), ty.view(1, -1, 1)).expand(shape), tx.view(1, 1, -1))
+    bad = int((got != want).sum().item())
+    assert bad == 0, (edge, bad)
+    del got, want
+    torch.cuda.empty_cache()
 
 
 def test_current_device_and_threads(edt, oracle):
