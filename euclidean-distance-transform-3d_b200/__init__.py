@@ -30,7 +30,7 @@ __version__ = "0.1.0"
 __all__ = [
   "edt", "edtsq", "sdf", "sdfsq",
   "edt1d", "edt1dsq", "edt2d", "edt2dsq", "edt3d", "edt3dsq",
-  "edt_cuda", "each", "each_cuda", "device_count", "library_path", "EDTError",
+  "edt_cuda", "transform_batch", "each", "each_cuda", "device_count", "library_path", "EDTError",
 ]
 
 FLAG_SQRT = 1
@@ -68,6 +68,8 @@ def _lib():
   lib.edtb200_device_count.restype = ci
   lib.edtb200_transform.argtypes = [vp, ci, ci, i64, i64, i64, f32, f32, f32, ci, ci, vp, ci, vp]
   lib.edtb200_transform.restype = ci
+  lib.edtb200_transform_batch.argtypes = [vp, vp, ci, ci, ci, i64, i64, i64, f32, f32, f32, ci, ci, ci]
+  lib.edtb200_transform_batch.restype = ci
   lib.edtb200_transform_voxel_graph.argtypes = [vp, ci, vp, ci, i64, i64, i64, f32, f32, f32, ci, ci, vp, ci, vp]
   lib.edtb200_transform_voxel_graph.restype = ci
   lib.edtb200_pass_first.argtypes = [vp, ci, i64, i64, i64, f32, ci, ci, vp, ci, vp]
@@ -349,6 +351,65 @@ def edt_cuda(labels, anisotropy=None, black_border=False, *, sqrt=False, signed=
     labels.data_ptr(), nbytes, nd, sx, sy, sz, wx, wy, wz, int(bool(black_border)), flags,
     out.data_ptr(), labels.device.index, ctypes.c_void_p(stream)))
   return out
+
+
+def transform_batch(volumes, anisotropy=None, black_border=False, *, sqrt=False, signed=False, outs=None,
+                    device=0):
+  """edtsq (or edt / sdfsq / sdf via `sqrt` / `signed`) of many arrays of ONE shape, dtype and
+  memory order -- e.g. the chunks of a dataset -- pipelined through the GPU: the upload of chunk
+  k+1 and the download of chunk k-1 overlap the transform of chunk k (`edtb200_transform_batch`).
+  Returns a list of float32 arrays (the arrays of `outs`, if given: same shape and order as the
+  inputs, float32; pass pinned buffers, e.g. `torch.empty(..., pin_memory=True).numpy()`, to let
+  the copies run at the PCIe rate).  Each result equals the single-call function's."""
+  vols = [np.asarray(v) for v in volumes]
+  if not vols:
+    return []
+  first = vols[0]
+  if first.ndim < 1 or first.ndim > 3:
+    raise TypeError("Multi-Label EDT library only supports up to 3 dimensions got {}.".format(first.ndim))
+  order = "F" if first.flags.f_contiguous else "C"
+  fixed = []
+  for v in vols:
+    if v.shape != first.shape or v.dtype != first.dtype:
+      raise ValueError("transform_batch: all volumes must share one shape and dtype")
+    if order == "F" and not v.flags.f_contiguous:
+      v = np.asfortranarray(v)
+    elif order == "C" and not v.flags.c_contiguous:
+      v = np.ascontiguousarray(v)
+    fixed.append(v)
+  if outs is None:
+    outs = [np.empty(first.shape, dtype=np.float32, order=order) for _ in fixed]
+  else:
+    outs = list(outs)
+    if len(outs) != len(fixed):
+      raise ValueError("transform_batch: one output array per volume")
+    for o in outs:
+      ok = isinstance(o, np.ndarray) and o.dtype == np.float32 and o.shape == first.shape and \
+          (o.flags.f_contiguous if order == "F" else o.flags.c_contiguous) and o.flags.writeable
+      if not ok:
+        raise ValueError("transform_batch: outs must be writable float32 arrays shaped and ordered like the volumes")
+  if first.size == 0:
+    for o in outs:
+      o[...] = 0
+    return outs
+  views = [_label_view(v) for v in fixed]
+  if views[0] is None:                      # dtype the reference does not dispatch on: zeros
+    for o in outs:
+      o[...] = 0
+    return outs
+  nd = first.ndim
+  if anisotropy is None:
+    anisotropy = (1.0,) * nd
+  elif nd == 1 and np.ndim(anisotropy) == 0:
+    anisotropy = (float(anisotropy),)
+  (sx, sy, sz), (wx, wy, wz) = _x_fastest(first.shape, anisotropy, order == "F")
+  n = len(views)
+  lab_ptrs = (ctypes.c_void_p * n)(*[v.ctypes.data for v in views])
+  out_ptrs = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+  flags = (FLAG_SQRT if sqrt else 0) | (FLAG_SIGNED if signed else 0)
+  _check(_lib().edtb200_transform_batch(lab_ptrs, out_ptrs, n, views[0].dtype.itemsize, nd, sx, sy, sz,
+                                        wx, wy, wz, int(bool(black_border)), flags, int(device)))
+  return outs
 
 
 # ---------------------------------------------------------------------------------------

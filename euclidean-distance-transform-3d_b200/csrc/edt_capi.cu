@@ -70,6 +70,13 @@ struct DeviceCache {
   float* dist = nullptr;
   size_t dist_bytes = 0;
   cudaStream_t stream = nullptr;
+  // second slot + copy streams + events of edtb200_transform_batch (slot 0 is labels / dist above)
+  void* labels2 = nullptr;
+  size_t labels2_bytes = 0;
+  float* dist2 = nullptr;
+  size_t dist2_bytes = 0;
+  cudaStream_t stream_up = nullptr, stream_down = nullptr;
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
   // step tables T[k] of the first-axis pass, keyed by the weight's bits (see step_table_kernel)
   struct Table { float* data = nullptr; int count = 0; uint32_t wbits = 0; cudaEvent_t ready = nullptr;
                  cudaStream_t built_on = nullptr; uint64_t stamp = 0; };
@@ -137,9 +144,13 @@ class CopyPool {
   bool stop_ = false;
 };
 
-CopyPool* g_pool = nullptr;           // created on first use, under g_mutex
+// Two pools and two sets of staging buffers: [0] for copies towards the device, [1] for copies
+// back, so that a batch (edtb200_transform_batch) can drive both directions at once from two
+// host threads.  Created on first use; only ever touched under g_mutex or by the batch's helper.
+CopyPool* g_pools[2] = {nullptr, nullptr};
 
-void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+void parallel_memcpy(void* dst, const void* src, size_t bytes, int dir) {
+  CopyPool*& g_pool = g_pools[dir];
   if (!g_pool) {
     unsigned hw = std::thread::hardware_concurrency();
     // measured on the B200 host (2 x 64 threads), 512 MiB each way: 8 threads 40 ms, 16 threads
@@ -164,7 +175,7 @@ struct StageBuffers {
   void* buf[kStages] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev[kStages] = {nullptr, nullptr, nullptr};
 };
-StageBuffers g_stage[kMaxDevices];
+StageBuffers g_stage[2][kMaxDevices];
 
 bool host_pointer_is_pinned(const void* p) {
   cudaPointerAttributes a;
@@ -172,8 +183,8 @@ bool host_pointer_is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-int ensure_stage(int device) {
-  StageBuffers& sb = g_stage[device];
+int ensure_stage(int device, int dir) {
+  StageBuffers& sb = g_stage[dir][device];
   for (int i = 0; i < kStages; ++i) {
     if (!sb.buf[i]) CUDA_TRY(cudaHostAlloc(&sb.buf[i], kStageBytes, cudaHostAllocDefault));
     if (!sb.ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&sb.ev[i], cudaEventDisableTiming));
@@ -187,15 +198,15 @@ int upload(void* dst_dev, const void* src_host, size_t bytes, int device, cudaSt
     CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream));
     return 0;
   }
-  int rc = ensure_stage(device);
+  int rc = ensure_stage(device, 0);
   if (rc) return rc;
-  StageBuffers& sb = g_stage[device];
+  StageBuffers& sb = g_stage[0][device];
   size_t off = 0;
   for (int k = 0; off < bytes; ++k) {
     const int b = k % kStages;
     const size_t n = bytes - off < kStageBytes ? bytes - off : kStageBytes;
     if (k >= kStages) CUDA_TRY(cudaEventSynchronize(sb.ev[b]));      // DMA out of this buffer finished
-    parallel_memcpy(sb.buf[b], static_cast<const char*>(src_host) + off, n);
+    parallel_memcpy(sb.buf[b], static_cast<const char*>(src_host) + off, n, 0);
     CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dst_dev) + off, sb.buf[b], n, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaEventRecord(sb.ev[b], stream));
     off += n;
@@ -209,9 +220,9 @@ int download(void* dst_host, const void* src_dev, size_t bytes, int device, cuda
     CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
     return 0;
   }
-  int rc = ensure_stage(device);
+  int rc = ensure_stage(device, 1);
   if (rc) return rc;
-  StageBuffers& sb = g_stage[device];
+  StageBuffers& sb = g_stage[1][device];
   size_t off = 0, prev_off = 0, prev_n = 0;
   int prev_b = -1;
   for (int k = 0; off < bytes || prev_b >= 0; ++k) {
@@ -225,7 +236,7 @@ int download(void* dst_host, const void* src_dev, size_t bytes, int device, cuda
     }
     if (prev_b >= 0) {                                             // drain the chunk queued one step earlier
       CUDA_TRY(cudaEventSynchronize(sb.ev[prev_b]));
-      parallel_memcpy(static_cast<char*>(dst_host) + prev_off, sb.buf[prev_b], prev_n);
+      parallel_memcpy(static_cast<char*>(dst_host) + prev_off, sb.buf[prev_b], prev_n, 1);
     }
     prev_b = b; prev_off = off; prev_n = n;
     off += n;
@@ -719,6 +730,124 @@ int edtb200_transform(const void* labels, int label_bytes, int ndim, int64_t sx,
   return 0;
 }
 
+int edtb200_transform_batch(const void* const* labels, float* const* outs, int count, int label_bytes, int ndim,
+                            int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
+                            int black_border, int flags, int device) {
+  if (count < 0) return fail(EDTB200_EINVAL, "negative count");
+  if (flags & (EDTB200_LABELS_ON_DEVICE | EDTB200_OUT_ON_DEVICE))
+    return fail(EDTB200_EINVAL, "edtb200_transform_batch pipelines HOST buffers; device-resident volumes are "
+                                "already asynchronous through edtb200_transform");
+  int rc = check_dims(label_bytes, ndim, sx, sy, sz);
+  if (rc) return rc;
+  const int64_t total = sx * sy * sz;
+  if (total == 0 || count == 0) return 0;
+  if (!labels || !outs) return fail(EDTB200_EINVAL, "null pointer");
+  for (int k = 0; k < count; ++k)
+    if (!labels[k] || !outs[k]) return fail(EDTB200_EINVAL, "null pointer in volume %d", k);
+
+  std::lock_guard<std::mutex> lock(g_mutex);
+  DeviceGuard restore_device;
+  DeviceCache* dcp = nullptr;
+  rc = probe(device, &dcp);
+  if (rc) return rc;
+  DeviceCache& dc = *dcp;
+  const size_t lab_bytes = (size_t)total * (size_t)label_bytes, out_bytes = (size_t)total * sizeof(float);
+  auto grow = [](void** p, size_t* have, size_t need) -> cudaError_t {
+    if (*have >= need) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *have = 0;
+    cudaError_t e = cudaMalloc(p, need);
+    if (e == cudaSuccess) *have = need;
+    return e;
+  };
+  CUDA_TRY(grow(&dc.labels, &dc.labels_bytes, lab_bytes));
+  CUDA_TRY(grow(reinterpret_cast<void**>(&dc.dist), &dc.dist_bytes, out_bytes));
+  if (count > 1) {
+    CUDA_TRY(grow(&dc.labels2, &dc.labels2_bytes, lab_bytes));
+    CUDA_TRY(grow(reinterpret_cast<void**>(&dc.dist2), &dc.dist2_bytes, out_bytes));
+  }
+  if (!dc.stream) CUDA_TRY(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking));
+  if (!dc.stream_up) CUDA_TRY(cudaStreamCreateWithFlags(&dc.stream_up, cudaStreamNonBlocking));
+  if (!dc.stream_down) CUDA_TRY(cudaStreamCreateWithFlags(&dc.stream_down, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    if (!dc.ev_up[i]) CUDA_TRY(cudaEventCreateWithFlags(&dc.ev_up[i], cudaEventDisableTiming));
+    if (!dc.ev_comp[i]) CUDA_TRY(cudaEventCreateWithFlags(&dc.ev_comp[i], cudaEventDisableTiming));
+    if (!dc.ev_down[i]) CUDA_TRY(cudaEventCreateWithFlags(&dc.ev_down[i], cudaEventDisableTiming));
+  }
+  void* d_labels[2] = {dc.labels, dc.labels2};
+  float* d_dist[2] = {dc.dist, dc.dist2};
+  const int border = black_border != 0;
+
+  // Volume k uses slot k % 2.  Three streams: uploads (fed by a helper thread, so that pageable
+  // buffers can be staged in both directions at once), the passes, downloads (this thread).
+  //   upload k    waits for the passes of k-2 (they read the slot's labels)
+  //   passes k    wait for upload k and for download k-2 (it reads the slot's distances)
+  //   download k  waits for the passes of k
+  // Host-side counters make sure an event has been RECORDED before someone waits on it.
+  std::mutex m;
+  std::condition_variable cv;
+  int uploads_queued = 0, passes_queued = 0, failed = 0;
+  char upload_error[sizeof(g_error)] = "";
+  std::thread uploader([&] {
+    cudaSetDevice(device);
+    for (int k = 0; k < count; ++k) {
+      const int slot = k & 1;
+      int urc = 0;
+      if (k >= 2) {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [&] { return passes_queued >= k - 1 || failed; });
+        if (failed) return;
+        if (cudaStreamWaitEvent(dc.stream_up, dc.ev_comp[slot], 0) != cudaSuccess) urc = EDTB200_ECUDA;
+      }
+      if (!urc) urc = upload(d_labels[slot], labels[k], lab_bytes, device, dc.stream_up);
+      if (!urc && cudaEventRecord(dc.ev_up[slot], dc.stream_up) != cudaSuccess) urc = EDTB200_ECUDA;
+      std::lock_guard<std::mutex> l(m);
+      if (urc) {
+        failed = urc;
+        snprintf(upload_error, sizeof(upload_error), "upload of volume %d failed: %.400s", k,
+                 urc == EDTB200_ECUDA ? cudaGetErrorString(cudaGetLastError()) : g_error);
+      } else {
+        uploads_queued = k + 1;
+      }
+      cv.notify_all();
+      if (urc) return;
+    }
+  });
+  auto bail = [&](int code) {
+    { std::lock_guard<std::mutex> l(m); if (!failed) failed = code; }
+    cv.notify_all();
+    uploader.join();
+    cudaStreamSynchronize(dc.stream_up); cudaStreamSynchronize(dc.stream); cudaStreamSynchronize(dc.stream_down);
+    return code;
+  };
+  #define BATCH_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+      fail(EDTB200_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); return bail(EDTB200_ECUDA); } } while (0)
+  for (int k = 0; k < count; ++k) {
+    const int slot = k & 1;
+    {
+      std::unique_lock<std::mutex> l(m);
+      cv.wait(l, [&] { return uploads_queued >= k + 1 || failed; });
+      if (failed) { l.unlock(); uploader.join(); cudaDeviceSynchronize(); return fail(failed, "%s", upload_error); }
+    }
+    BATCH_TRY(cudaStreamWaitEvent(dc.stream, dc.ev_up[slot], 0));
+    if (k >= 2) BATCH_TRY(cudaStreamWaitEvent(dc.stream, dc.ev_down[slot], 0));
+    rc = run_passes(d_labels[slot], label_bytes, ndim, sx, sy, sz, wx, wy, wz, border, flags, d_dist[slot], dc,
+                    dc.stream);
+    if (rc) return bail(rc);
+    BATCH_TRY(cudaEventRecord(dc.ev_comp[slot], dc.stream));
+    { std::lock_guard<std::mutex> l(m); passes_queued = k + 1; }
+    cv.notify_all();
+    BATCH_TRY(cudaStreamWaitEvent(dc.stream_down, dc.ev_comp[slot], 0));
+    rc = download(outs[k], d_dist[slot], out_bytes, device, dc.stream_down);
+    if (rc) return bail(rc);
+    BATCH_TRY(cudaEventRecord(dc.ev_down[slot], dc.stream_down));
+  }
+  #undef BATCH_TRY
+  uploader.join();
+  CUDA_TRY(cudaStreamSynchronize(dc.stream_down));
+  return 0;
+}
+
 int edtb200_transform_voxel_graph(const void* labels, int label_bytes, const unsigned char* graph, int ndim,
                                   int64_t sx, int64_t sy, int64_t sz, float wx, float wy, float wz,
                                   int black_border, int flags, float* out, int device, void* stream_v) {
@@ -931,7 +1060,7 @@ int edtb200_release(void) {
   if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
   for (int d = 0; d < count && d < kMaxDevices; ++d) {
     DeviceCache& dc = g_cache[d];
-    bool any = dc.labels || dc.dist || dc.stream;
+    bool any = dc.labels || dc.dist || dc.stream || dc.labels2 || dc.dist2 || dc.stream_up;
     for (auto& t : dc.tables) any = any || t.data;
     if (!any) continue;
     cudaSetDevice(d);
@@ -940,15 +1069,25 @@ int edtb200_release(void) {
     if (dc.stream) { cudaStreamSynchronize(dc.stream); cudaStreamDestroy(dc.stream); }
     if (dc.labels) cudaFree(dc.labels);
     if (dc.dist) cudaFree(dc.dist);
+    if (dc.labels2) cudaFree(dc.labels2);
+    if (dc.dist2) cudaFree(dc.dist2);
+    if (dc.stream_up) cudaStreamDestroy(dc.stream_up);
+    if (dc.stream_down) cudaStreamDestroy(dc.stream_down);
+    for (int i = 0; i < 2; ++i) {
+      if (dc.ev_up[i]) cudaEventDestroy(dc.ev_up[i]);
+      if (dc.ev_comp[i]) cudaEventDestroy(dc.ev_comp[i]);
+      if (dc.ev_down[i]) cudaEventDestroy(dc.ev_down[i]);
+    }
     dc = DeviceCache();
   }
-  for (int d = 0; d < count && d < kMaxDevices; ++d) {
-    StageBuffers& sb = g_stage[d];
-    for (int i = 0; i < kStages; ++i) {
-      if (sb.buf[i]) { cudaFreeHost(sb.buf[i]); sb.buf[i] = nullptr; }
-      if (sb.ev[i]) { cudaEventDestroy(sb.ev[i]); sb.ev[i] = nullptr; }
+  for (int dir = 0; dir < 2; ++dir)
+    for (int d = 0; d < count && d < kMaxDevices; ++d) {
+      StageBuffers& sb = g_stage[dir][d];
+      for (int i = 0; i < kStages; ++i) {
+        if (sb.buf[i]) { cudaFreeHost(sb.buf[i]); sb.buf[i] = nullptr; }
+        if (sb.ev[i]) { cudaEventDestroy(sb.ev[i]); sb.ev[i] = nullptr; }
+      }
     }
-  }
   return 0;
 }
 

@@ -81,6 +81,19 @@ int edtb200_transform(const void *labels, int label_bytes, int ndim,
                       int black_border, int flags,
                       float *out, int device, void *stream);
 
+/* Many volumes of one geometry, HOST buffers, pipelined: while volume k is being transformed,
+ * volume k+1 is on its way to the device and volume k-1 on its way back (two device slots,
+ * separate copy streams, PCIe used in both directions at once).  This is what a caller of the
+ * reference does in a loop over the chunks of a dataset (README.md:191, the skeletonisation use
+ * case); per volume the result is exactly what edtb200_transform returns.
+ *   labels[k], outs[k]  host pointers (pinned memory is copied directly, pageable memory is staged
+ *                       by two groups of host threads); outs[k] must not alias any labels[j]
+ *   flags               EDTB200_SQRT / EDTB200_SIGNED; the *_ON_DEVICE flags are rejected
+ * Returns when every result has landed. */
+int edtb200_transform_batch(const void *const *labels, float *const *outs, int count,
+                            int label_bytes, int ndim, int64_t sx, int64_t sy, int64_t sz,
+                            float wx, float wy, float wz, int black_border, int flags, int device);
+
 /* Transform under a voxel connectivity graph (2-D or 3-D only).
  *
  * Replaces  pyedt::_edt2dsq_voxel_graph<T, uint8_t>   src/edt_voxel_graph.hpp:54-123

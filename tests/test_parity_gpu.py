@@ -483,6 +483,35 @@ def test_cfg4_1024_device_resident(edt):
   assert bool((edt.edt_cuda(lab, (4.0, 4.0, 4.0)) == base * 16.0).all())
 
 
+def test_transform_batch_pipeline(edt, oracle):
+  """edtb200_transform_batch: many host volumes through two device slots; every result must equal
+  the single-call result (and the oracle's), for pageable and pinned buffers, odd counts, count 1."""
+  import torch
+  rng = np.random.default_rng(41)
+  shape = (70, 96, 130)                      # 3.5 MB of uint32: above the direct-copy threshold for float32 too
+  vols = [cases.random_volume(rng, shape, kind, np.uint32) for kind in ("blocks", "iid", "balls", "few", "blocks")]
+  vols = [np.asfortranarray(v) for v in vols]
+  for count in (5, 1, 2):
+    got = edt.transform_batch(vols[:count], (2.0, 1.0, 3.0), True, sqrt=True)
+    assert len(got) == count
+    for v, g in zip(vols, got):
+      assert g.flags.f_contiguous
+      assert_same(g, oracle.edt(v, anisotropy=(2.0, 1.0, 3.0), black_border=True), ("batch", count))
+  # bigger volumes (staged copies, 3 x 32 MiB buffers per direction), pageable and pinned outputs
+  big = [np.ascontiguousarray(rng.integers(0, 5, (160, 256, 320), dtype=np.int64).astype(np.uint16)) for _ in range(4)]
+  want = [edt.sdfsq(v, anisotropy=(1.0, 2.0, 1.0)) for v in big]
+  got = edt.transform_batch(big, (1.0, 2.0, 1.0), signed=True)
+  pinned = [torch.empty(big[0].shape, dtype=torch.float32, pin_memory=True).numpy() for _ in big]
+  got_pinned = edt.transform_batch(big, (1.0, 2.0, 1.0), signed=True, outs=pinned)
+  for w, g, gp in zip(want, got, got_pinned):
+    assert_same(g, w, "batch pageable")
+    assert_same(gp, w, "batch pinned")
+  assert got_pinned[0] is pinned[0]
+  assert edt.transform_batch([]) == []
+  with pytest.raises(ValueError):
+    edt.transform_batch([vols[0], vols[1][:10]])
+
+
 def test_more_than_2_31_voxels(edt):
   """528 x 2048 x 2048 = 2.2e9 voxels (64-bit voxel indices everywhere), device-resident, against
   closed forms: isolated boxes of edge 48 (long runs: chunk hulls + stitching) and 16 (short runs),
