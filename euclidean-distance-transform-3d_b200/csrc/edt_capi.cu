@@ -205,7 +205,9 @@ int upload(void* dst_dev, const void* src_host, size_t bytes, int device, cudaSt
   for (int k = 0; off < bytes; ++k) {
     const int b = k % kStages;
     const size_t n = bytes - off < kStageBytes ? bytes - off : kStageBytes;
-    if (k >= kStages) CUDA_TRY(cudaEventSynchronize(sb.ev[b]));      // DMA out of this buffer finished
+    // the DMA out of this buffer must have finished -- also the one queued by an EARLIER upload:
+    // inside a batch the previous volume's copies may still be waiting in the stream
+    CUDA_TRY(cudaEventSynchronize(sb.ev[b]));
     parallel_memcpy(sb.buf[b], static_cast<const char*>(src_host) + off, n, 0);
     CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dst_dev) + off, sb.buf[b], n, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaEventRecord(sb.ev[b], stream));
