@@ -19,7 +19,9 @@ thread pool); keyword-only ``device=`` selects the GPU; ``sdf``/``sdfsq`` run ON
 transform (background treated as a label, sign applied in the last store) instead of two;
 ``voxel_graph=`` (2-D / 3-D, src/edt.pyx:514-620, 736-844) draws the doubled grid and runs
 the transform on the device.
-``edt_cuda`` transforms a torch CUDA tensor without touching host memory.
+``edt_cuda`` transforms a torch CUDA tensor without touching host memory, and every function
+above accepts device-resident input directly (a torch CUDA tensor or any object exposing
+``__cuda_array_interface__``) and then returns a torch CUDA tensor.
 """
 import ctypes
 import os
@@ -188,8 +190,74 @@ def _transform_voxel_graph_host(data, voxel_graph, anisotropy, black_border, fla
   return out.reshape(data.shape, order=order)
 
 
+def _device_array(data):
+  """torch CUDA tensor view of `data` if it already lives on a GPU (a torch CUDA tensor, or any
+  object exposing `__cuda_array_interface__`: CuPy, Numba, ...), else None.  Zero-copy."""
+  if isinstance(data, (np.ndarray, list, tuple)) or np.isscalar(data):
+    return None
+  mod = type(data).__module__
+  if mod.startswith("torch"):
+    return data if getattr(data, "is_cuda", False) else None
+  if hasattr(data, "__cuda_array_interface__"):
+    import torch
+    return torch.as_tensor(data, device="cuda")
+  return None
+
+
+def _front_door_device(t, anisotropy, black_border, voxel_graph, flags, fixed_dims):
+  """Device-resident input to the reference-named functions: same semantics, result returned as a
+  torch CUDA tensor (which itself exports DLPack and `__cuda_array_interface__`).  A Fortran-ordered
+  array is transformed through its transposed (C-ordered) view with the anisotropy reversed, which
+  is exactly the axis mapping of src/edt.pyx:651-664, so the memory order is preserved without a copy."""
+  import torch
+  dims = t.dim()
+  if fixed_dims is not None and dims != fixed_dims:
+    raise ValueError("expected a %d-D array, got %d-D" % (fixed_dims, dims))
+  if dims > 3:
+    raise TypeError("Multi-Label EDT library only supports up to 3 dimensions got {}.".format(dims))
+  if voxel_graph is not None and dims not in (2, 3):
+    raise TypeError("Voxel connectivity graph is only supported for 2D and 3D. Got {}.".format(dims))
+  if t.numel() == 0:
+    return torch.zeros(t.shape, dtype=torch.float32, device=t.device)
+  if t.dtype in (torch.float32, torch.float64):
+    # labels compare by value (src/edt.pyx:704-722): fold -0.0 onto +0.0, then use the raw bits
+    t = (t + 0).view(torch.int32 if t.dtype == torch.float32 else torch.int64)
+  if anisotropy is None:
+    anisotropy = (1.0,) * dims
+  elif np.ndim(anisotropy) == 0:
+    anisotropy = (float(anisotropy),)
+  else:
+    anisotropy = tuple(float(a) for a in anisotropy)
+  if len(anisotropy) != dims:
+    raise ValueError("anisotropy must have one entry per dimension")
+  fortran = dims > 1 and not t.is_contiguous() and t.permute(*reversed(range(dims))).is_contiguous()
+  if fortran:
+    t = t.permute(*reversed(range(dims)))
+    anisotropy = tuple(reversed(anisotropy))
+  graph = None
+  if voxel_graph is not None:
+    graph = _device_array(voxel_graph)
+    if graph is None:
+      graph = torch.as_tensor(np.ascontiguousarray(voxel_graph), device=t.device)
+    if graph.dtype not in (torch.uint8, torch.int8):
+      graph = graph.to(torch.uint8)
+    if fortran:
+      graph = graph.permute(*reversed(range(dims)))
+    graph = graph.contiguous()
+  sqrt, signed = bool(flags & FLAG_SQRT), bool(flags & FLAG_SIGNED)
+  if graph is not None and signed:       # f(data) - f(data == 0), src/edt.pyx:147-158
+    out = edt_cuda(t, anisotropy, black_border, sqrt=sqrt, voxel_graph=graph)
+    out -= edt_cuda(t == 0, anisotropy, black_border, sqrt=sqrt, voxel_graph=graph)
+  else:
+    out = edt_cuda(t, anisotropy, black_border, sqrt=sqrt, signed=signed, voxel_graph=graph)
+  return out.permute(*reversed(range(dims))) if fortran else out
+
+
 def _front_door(data, anisotropy, black_border, voxel_graph, flags, device, fixed_dims=None):
   """Argument handling of edtsq(), src/edt.pyx:276-310."""
+  on_device = _device_array(data)
+  if on_device is not None:
+    return _front_door_device(on_device, anisotropy, black_border, voxel_graph, flags, fixed_dims)
   if isinstance(data, list):
     data = np.array(data)
   data = np.asarray(data)

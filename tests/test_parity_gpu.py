@@ -285,6 +285,27 @@ def test_torch_device_path(edt, oracle):
   assert again.data_ptr() == out.data_ptr()
   u8 = torch.from_numpy((lab != 0)).cuda()
   assert_same(edt.edt_cuda(u8).cpu().numpy(), oracle.edtsq(lab != 0), "bool tensor")
+  # the reference-named functions take device-resident input as it is and answer on the device
+  got = edt.sdf(t, anisotropy=(2.0, 3.0, 5.0), black_border=True)
+  assert isinstance(got, torch.Tensor) and got.is_cuda
+  assert_same(got.cpu().numpy(), oracle.sdf(lab, anisotropy=(2.0, 3.0, 5.0), black_border=True), "sdf(tensor)")
+
+  class Foreign:                         # e.g. a CuPy / Numba array: only __cuda_array_interface__
+    def __init__(self, tensor):
+      self.keep = tensor
+      self.__cuda_array_interface__ = tensor.__cuda_array_interface__
+
+  flab = np.asfortranarray(lab.astype(np.float32) - 1.0)          # float labels, Fortran order, a -0.0 or two
+  flab[flab == 0] = -0.0
+  ft = torch.from_numpy(flab).cuda()
+  assert ft.stride() == torch.from_numpy(flab).stride()
+  got = edt.edtsq(Foreign(ft), anisotropy=(2.0, 3.0, 5.0))
+  assert got.is_cuda and got.stride() == ft.stride()               # memory order preserved, no copy
+  assert_same(got.cpu().numpy(), oracle.edtsq(flab, anisotropy=(2.0, 3.0, 5.0)), "edtsq(F-ordered device array)")
+  plane, graph = lab[3] != 0, np.full(lab[3].shape, 63, np.uint8)
+  graph[::3, ::4] = 0b111010
+  got = edt.edt(torch.from_numpy(plane).cuda(), black_border=True, voxel_graph=torch.from_numpy(graph).cuda())
+  assert_same(got.cpu().numpy(), oracle.edt(plane, black_border=True, voxel_graph=graph), "edt(tensor, voxel_graph)")
 
 
 def test_per_axis_entry_points(edt, oracle):
