@@ -192,8 +192,17 @@ def cpu_baseline_leg():
   t0 = time.perf_counter()
   ref.edtsq(sample, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
   dt = time.perf_counter() - t0
-  return {"value": sample.size / dt / 1e6, "unit": "Mvoxels/s", "cores": cores, "kind": kind,
-          "sample": "one edtsq of a 512x512x%d Z slab of the workload (%.1f s), parallel=%d" % (depth, dt, cores)}
+  out = {"value": sample.size / dt / 1e6, "unit": "Mvoxels/s", "cores": cores, "kind": kind,
+         "sample": "one edtsq of a 512x512x%d Z slab of the workload (%.1f s), parallel=%d" % (depth, dt, cores)}
+  if cores > 1:
+    # the same code on ONE thread (SURVEY.md section 8d asks for both), on a thinner slab
+    thin = np.asfortranarray(labels[:, :, :max(32, depth // 8)])
+    t0 = time.perf_counter()
+    ref.edtsq(thin, anisotropy=ANISOTROPY, black_border=False, parallel=1)
+    dt1 = time.perf_counter() - t0
+    out["single_thread"] = {"value": thin.size / dt1 / 1e6, "unit": "Mvoxels/s",
+                            "sample": "512x512x%d slab (%.1f s), parallel=1" % (thin.shape[2], dt1)}
+  return out
 
 
 def ours(args):
