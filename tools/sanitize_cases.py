@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""A few small transforms that touch every kernel variant, for runs under compute-sanitizer:
+  compute-sanitizer --tool memcheck  python tools/sanitize_cases.py
+  compute-sanitizer --tool racecheck python tools/sanitize_cases.py
+Results are still compared with the oracle, so a sanitizer-induced slowdown cannot hide a wrong answer."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+import edt_b200 as edt  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+rng = np.random.default_rng(3)
+done = 0
+
+
+def check(name, got, want):
+  global done
+  assert np.array_equal(got, want, equal_nan=True), name
+  done += 1
+
+
+# vector X pass + TMA tile kernel (sx % 4 == 0), short / long runs, all epilogues
+for kind in ("iid", "blocks", "balls"):
+  lab = np.asfortranarray(cases.random_volume(rng, (64, 80, 72), kind, np.uint32))
+  check("edtsq " + kind, edt.edtsq(lab, anisotropy=(1, 2, 3)), oracle.edtsq(lab, anisotropy=(1, 2, 3)))
+  check("sdf " + kind, edt.sdf(lab, anisotropy=(1, 2, 3), black_border=True),
+        oracle.sdf(lab, anisotropy=(1, 2, 3), black_border=True))
+# generic X pass + plain-load tile kernel (odd sizes), every label width
+for dtype in (np.uint8, np.uint16, np.uint64):
+  lab = np.asfortranarray(cases.random_volume(rng, (37, 45, 51), "blocks", dtype))
+  check("odd " + np.dtype(dtype).name, edt.edt(lab, anisotropy=(0.7, 1.3, 2.9)), oracle.edt(lab, anisotropy=(0.7, 1.3, 2.9)))
+# long runs across many chunks (stitching stage), 2-D and 1-D drivers
+lab = np.ones((8, 300, 12), dtype=np.uint8, order="F")
+lab[3, 150, 5] = 0
+check("long runs", edt.edtsq(lab), oracle.edtsq(lab))
+img = cases.random_volume(rng, (200, 130), "balls", np.uint16)
+check("2-D", edt.edt(img, black_border=True), oracle.edt(img, black_border=True))
+row = cases.random_volume(rng, (700,), "blocks", np.uint32)
+check("1-D", edt.edtsq(row, anisotropy=2.5), oracle.edtsq(row, anisotropy=2.5))
+# lines beyond the tile kernel (n > 4096): thread-per-line kernel
+tall = np.asfortranarray(cases.random_volume(rng, (8, 4200, 2), "blocks", np.uint8))
+check("n > 4096", edt.edtsq(tall), oracle.edtsq(tall))
+# voxel graph
+lab, graph, kw = cases.random_graph_case(7)
+check("voxel graph", edt.edtsq(lab, voxel_graph=graph, **kw), oracle.edtsq(lab, voxel_graph=graph, **kw))
+print("sanitize_cases: %d results equal to the oracle" % done)
