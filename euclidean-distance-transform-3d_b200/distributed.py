@@ -265,7 +265,10 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   hint_key = (id(group), tuple(labels_local.shape[1:]))
   remember = halo is None and method == "auto"
   if halo is None:
-    halo = _HALO_HINT.get(hint_key, 32) if method == "auto" else 32
+    if isinstance(peer_halo, PeerHalo):
+      halo = peer_halo.halo                  # an explicit staging buffer fixes the depth
+    else:
+      halo = _HALO_HINT.get(hint_key, 32) if method == "auto" else 32
   marks = info.get("marks") if isinstance(info, dict) else None      # optional CUDA-event phase marks
 
   def mark(name):
