@@ -4,8 +4,7 @@
 // src/edt.hpp:411-484, 632-678): it owns the pass order X -> Y -> Z over one float32
 // volume that is transformed in place, but the "thread pool" is the CUDA grid and the
 // passes are stream-ordered kernel launches.  No CPU fallback exists in this file.
-#include "../../include/edt_b200.h"
-#include "edt_kernels.cuh"
+#include "edt_host.h"
 #include "edt_voxel_graph.cuh"
 
 #include <cstdarg>
@@ -18,7 +17,8 @@
 #include <thread>
 #include <vector>
 
-namespace {
+namespace edtb200 {
+namespace host {
 
 thread_local char g_error[512] = "";
 
@@ -30,64 +30,112 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-#define CUDA_TRY(expr)                                                              \
-  do {                                                                              \
-    cudaError_t e__ = (expr);                                                       \
-    if (e__ != cudaSuccess)                                                         \
-      return fail(e__ == cudaErrorMemoryAllocation ? EDTB200_ENOMEM : EDTB200_ECUDA, \
-                  "%s failed: %s", #expr, cudaGetErrorString(e__));                 \
-  } while (0)
-
-constexpr int kMaxDevices = 64;
-
-// cuTensorMapEncodeTiled, fetched through the runtime so that libcuda is not a link-time
-// dependency (the library must load on machines without a driver, e.g. for the build check).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-bool g_encode_tried = false;
-
 EncodeTiledFn tensor_map_encoder() {
-  if (!g_encode_tried) {
-    g_encode_tried = true;
+  static std::once_flag once;
+  static EncodeTiledFn encode = nullptr;
+  std::call_once(once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+      encode = reinterpret_cast<EncodeTiledFn>(fn);
     else
       cudaGetLastError();
-  }
-  return g_encode;
+  });
+  return encode;
 }
 
-// Per-device cached state for calls that take host buffers.
-struct DeviceCache {
-  void* labels = nullptr;
-  size_t labels_bytes = 0;
-  float* dist = nullptr;
-  size_t dist_bytes = 0;
-  cudaStream_t stream = nullptr;
-  // second slot + copy streams + events of edtb200_transform_batch (slot 0 is labels / dist above)
-  void* labels2 = nullptr;
-  size_t labels2_bytes = 0;
-  float* dist2 = nullptr;
-  size_t dist2_bytes = 0;
-  cudaStream_t stream_up = nullptr, stream_down = nullptr;
-  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
-  // step tables T[k] of the first-axis pass, keyed by the weight's bits (see step_table_kernel)
-  struct Table { float* data = nullptr; int count = 0; uint32_t wbits = 0; cudaEvent_t ready = nullptr;
-                 cudaStream_t built_on = nullptr; uint64_t stamp = 0; };
-  Table tables[8];
-  uint64_t table_clock = 0;
-  int sm_count = 0;
-  int max_smem_optin = 0;
-  bool probed = false;
-};
+size_t tile_smem_bytes(int n, int tx, int rows_alloc) {
+  const int nchunks = (n + 31) >> 5;
+  return (size_t)rows_alloc * tx * 4 + (size_t)nchunks * tx * 12 + (size_t)((n + 3) & ~1) * 4 + 16 +
+         (size_t)nchunks * tx;     // + one flag byte per (chunk, line)
+}
 
-std::mutex g_mutex;
+// Will launch_later() take the shared-memory tile kernel for this geometry?  (same conditions)
+bool tile_path_ok(const LineGeom& g, const DeviceCache& dc) {
+  if (!((int64_t)g.n * g.line_stride + 64 < (1LL << 32) && g.n <= 4096 && g.inner_count < (1LL << 31))) return false;
+  const int nb = (g.n + 255) / 256;
+  int br = (g.n + nb - 1) / nb;
+  if (nb > 1) br = (br + 3) & ~3;
+  return tile_smem_bytes(g.n, 8, br * nb) <= (size_t)dc.max_smem_optin;
+}
+
+cudaError_t scratch_alloc(DeviceCache& dc, void** p, size_t bytes, cudaStream_t stream) {
+  if (dc.pool) return cudaMallocFromPoolAsync(p, bytes, dc.pool, stream);
+  return cudaMallocAsync(p, bytes, stream);
+}
+
+// Device table T[0..count) for weight w, cached per device.  Built once on `stream`; other
+// streams wait on the build event, so no host synchronisation and no per-call allocation.
+// When all slots are taken the least recently used table is retired: the retiring stream waits
+// for the last kernel of every stream that used the table (one event per user stream) and the
+// buffer is freed in stream order -- no device-wide synchronisation.
+int step_table(DeviceCache& dc, float w, int count, cudaStream_t stream, const float** out) {
+  std::lock_guard<std::mutex> guard(dc.lock);
+  uint32_t wbits;
+  memcpy(&wbits, &w, sizeof(wbits));
+  DeviceCache::Table* hit = nullptr;
+  DeviceCache::Table* victim = &dc.tables[0];
+  for (auto& t : dc.tables) {
+    if (t.data && t.wbits == wbits && t.count >= count) { hit = &t; break; }
+    if (t.stamp < victim->stamp) victim = &t;
+  }
+  if (!hit) {
+    DeviceCache::Table& t = *victim;
+    if (t.data) {
+      if (t.many_users) CUDA_TRY(cudaDeviceSynchronize());    // more user streams than tracked: rare
+      for (int u = 0; u < DeviceCache::Table::kUsers; ++u)
+        if (t.user_set[u]) CUDA_TRY(cudaStreamWaitEvent(stream, t.used[u], 0));
+      if (t.ready) CUDA_TRY(cudaStreamWaitEvent(stream, t.ready, 0));
+      CUDA_TRY(cudaFreeAsync(t.data, stream));
+      t.data = nullptr;
+      for (int u = 0; u < DeviceCache::Table::kUsers; ++u) t.user_set[u] = false;
+      t.many_users = false;
+    }
+    const int cap = count < 4096 ? 4096 : count;
+    CUDA_TRY(scratch_alloc(dc, reinterpret_cast<void**>(&t.data), sizeof(float) * (size_t)cap, stream));
+    if (!t.ready) CUDA_TRY(cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming));
+    step_table_kernel<<<1, 32, 0, stream>>>(w, cap, t.data);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(t.ready, stream));
+    t.count = cap; t.wbits = wbits; t.built_on = stream;
+    hit = &t;
+  } else if (hit->built_on != stream) {
+    CUDA_TRY(cudaStreamWaitEvent(stream, hit->ready, 0));
+  }
+  hit->stamp = ++dc.table_clock;
+  *out = hit->data;
+  return 0;
+}
+
+// Called after the kernel that reads table `data` has been queued on `stream`.
+int step_table_used(DeviceCache& dc, const float* data, cudaStream_t stream) {
+  std::lock_guard<std::mutex> guard(dc.lock);
+  for (auto& t : dc.tables) {
+    if (t.data != data) continue;
+    int slot = -1;
+    for (int u = 0; u < DeviceCache::Table::kUsers; ++u)
+      if (t.user_set[u] && t.user[u] == stream) { slot = u; break; }
+    if (slot < 0)
+      for (int u = 0; u < DeviceCache::Table::kUsers; ++u)
+        if (!t.user_set[u]) { slot = u; break; }
+    if (slot < 0) { t.many_users = true; return 0; }
+    if (!t.used[slot]) CUDA_TRY(cudaEventCreateWithFlags(&t.used[slot], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(t.used[slot], stream));
+    t.user[slot] = stream; t.user_set[slot] = true;
+    return 0;
+  }
+  return 0;
+}
+
+}  // namespace host
+}  // namespace edtb200
+
+namespace {
+
+using namespace edtb200::host;
+
+constexpr int kMaxDevices = 64;
 DeviceCache g_cache[kMaxDevices];
 
 // ---- host <-> device staging for pageable host memory --------------------------------
@@ -144,14 +192,17 @@ class CopyPool {
   bool stop_ = false;
 };
 
-// Two pools and two sets of staging buffers: [0] for copies towards the device, [1] for copies
-// back, so that a batch (edtb200_transform_batch) can drive both directions at once from two
-// host threads.  Created on first use; only ever touched under g_mutex or by the batch's helper.
-CopyPool* g_pools[2] = {nullptr, nullptr};
+// Per device, two pools and two sets of staging buffers: [0] for copies towards the device, [1]
+// for copies back, so that a batch (edtb200_transform_batch) can drive both directions at once
+// from two host threads, and calls on different devices never share a pool.  Created on first use
+// (under g_init); used only by the holder of the device's host_call lock and its batch helper.
+std::mutex g_init;
+CopyPool* g_pools[2][kMaxDevices] = {};
 
-void parallel_memcpy(void* dst, const void* src, size_t bytes, int dir) {
-  CopyPool*& g_pool = g_pools[dir];
+void parallel_memcpy(void* dst, const void* src, size_t bytes, int dir, int device) {
+  CopyPool*& g_pool = g_pools[dir][device];
   if (!g_pool) {
+    std::lock_guard<std::mutex> guard(g_init);
     unsigned hw = std::thread::hardware_concurrency();
     // measured on the B200 host (2 x 64 threads), 512 MiB each way: 8 threads 40 ms, 16 threads
     // 31 ms, 32 threads 38 ms per numpy-to-numpy call; populating the fresh output array's pages
@@ -208,7 +259,7 @@ int upload(void* dst_dev, const void* src_host, size_t bytes, int device, cudaSt
     // the DMA out of this buffer must have finished -- also the one queued by an EARLIER upload:
     // inside a batch the previous volume's copies may still be waiting in the stream
     CUDA_TRY(cudaEventSynchronize(sb.ev[b]));
-    parallel_memcpy(sb.buf[b], static_cast<const char*>(src_host) + off, n, 0);
+    parallel_memcpy(sb.buf[b], static_cast<const char*>(src_host) + off, n, 0, device);
     CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(dst_dev) + off, sb.buf[b], n, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaEventRecord(sb.ev[b], stream));
     off += n;
@@ -238,7 +289,7 @@ int download(void* dst_host, const void* src_dev, size_t bytes, int device, cuda
     }
     if (prev_b >= 0) {                                             // drain the chunk queued one step earlier
       CUDA_TRY(cudaEventSynchronize(sb.ev[prev_b]));
-      parallel_memcpy(static_cast<char*>(dst_host) + prev_off, sb.buf[prev_b], prev_n, 1);
+      parallel_memcpy(static_cast<char*>(dst_host) + prev_off, sb.buf[prev_b], prev_n, 1, device);
     }
     prev_b = b; prev_off = off; prev_n = n;
     off += n;
@@ -264,15 +315,27 @@ int probe(int device, DeviceCache** out) {
   if (device >= count) return fail(EDTB200_EINVAL, "device %d out of range (%d visible)", device, count);
   DeviceCache& dc = g_cache[device];
   CUDA_TRY(cudaSetDevice(device));
+  std::lock_guard<std::mutex> guard(dc.lock);
   if (!dc.probed) {
     CUDA_TRY(cudaDeviceGetAttribute(&dc.sm_count, cudaDevAttrMultiProcessorCount, device));
     CUDA_TRY(cudaDeviceGetAttribute(&dc.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    // keep stream-ordered allocations (the code plane, long-line temporaries) in the pool between
-    // calls instead of returning them to the driver at every synchronisation
-    cudaMemPool_t pool = nullptr;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    // Stream-ordered scratch (voxel-graph grids, long-line temporaries, step tables) comes from a
+    // PRIVATE pool: the process-wide default pool -- which the host application (PyTorch, CuPy)
+    // may share -- keeps its own settings.  The pool keeps up to EDTB200_POOL_KEEP_MB (default
+    // 1024) between calls so that repeated transforms do not go back to the driver;
+    // edtb200_release() trims it to nothing.
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&dc.pool, &props) == cudaSuccess) {
+      unsigned long long keep = 1024ull << 20;
+      if (const char* env = getenv("EDTB200_POOL_KEEP_MB")) keep = strtoull(env, nullptr, 10) << 20;
+      cudaMemPoolSetAttribute(dc.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+      dc.pool = nullptr;                 // fall back to the default pool, settings untouched
     }
     cudaGetLastError();
     dc.probed = true;
@@ -293,283 +356,23 @@ int check_dims(int label_bytes, int ndim, int64_t& sx, int64_t& sy, int64_t& sz)
   return 0;
 }
 
-// Device table T[0..count) for weight w, cached per device.  Built once on `stream`; other
-// streams wait on the build event, so no host synchronisation and no per-call allocation.
-int step_table(DeviceCache& dc, float w, int count, cudaStream_t stream, const float** out) {
-  uint32_t wbits;
-  memcpy(&wbits, &w, sizeof(wbits));
-  DeviceCache::Table* hit = nullptr;
-  DeviceCache::Table* victim = &dc.tables[0];
-  for (auto& t : dc.tables) {
-    if (t.data && t.wbits == wbits && t.count >= count) { hit = &t; break; }
-    if (t.stamp < victim->stamp) victim = &t;
-  }
-  if (!hit) {
-    DeviceCache::Table& t = *victim;
-    if (t.data) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(t.data); t.data = nullptr; }
-    const int cap = count < 4096 ? 4096 : count;
-    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&t.data), sizeof(float) * (size_t)cap));
-    if (!t.ready) CUDA_TRY(cudaEventCreateWithFlags(&t.ready, cudaEventDisableTiming));
-    edtb200::step_table_kernel<<<1, 32, 0, stream>>>(w, cap, t.data);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(t.ready, stream));
-    t.count = cap; t.wbits = wbits; t.built_on = stream;
-    hit = &t;
-  } else if (hit->built_on != stream) {
-    CUDA_TRY(cudaStreamWaitEvent(stream, hit->ready, 0));
-  }
-  hit->stamp = ++dc.table_clock;
-  *out = hit->data;
-  return 0;
-}
-
-// ---- launches ---------------------------------------------------------------------
-
-// codes != nullptr asks for the one-byte neighbour codes (see first_axis_vec_kernel); *codes_done
-// reports whether they were produced (only the vector kernel can).
-template <int Bytes>
-int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float w, int border,
-                 int flags, DeviceCache& dc, cudaStream_t stream, uint8_t* codes = nullptr, int64_t sy = 1,
-                 bool* codes_done = nullptr) {
-  if (codes_done) *codes_done = false;
-  using namespace edtb200;
-  const float* table = nullptr;
-  int trc = step_table(dc, w, (int)sx + 1, stream, &table);
-  if (trc) return trc;
-
-  using LT = typename LabelOf<Bytes>::type;
-  // register-resident vector kernel when rows are short and 16-byte aligned
-  if (sx % 4 == 0 && sx <= 1024 && reinterpret_cast<uintptr_t>(labels) % (4 * Bytes) == 0 &&
-      reinterpret_cast<uintptr_t>(f) % 16 == 0) {
-    const size_t smem = sizeof(float) * (size_t)(sx + 2);
-    int64_t blocks = (nlines + 7) / 8;
-    const int64_t cap = (int64_t)dc.sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    const LT* lab = static_cast<const LT*>(labels);
-    const bool want_codes = codes != nullptr && reinterpret_cast<uintptr_t>(codes) % 4 == 0;
-#define EDT_LAUNCH_VEC(KK)                                                                         \
-  do {                                                                                           \
-    if (want_codes) {                                                                            \
-      if (flags == 0)                                                                            \
-        first_axis_vec_kernel<Bytes, KK, true, true><<<(unsigned)blocks, 256, smem, stream>>>(    \
-            lab, f, nlines, (int)sx, table, border, flags, codes, (int)sy);                      \
-      else                                                                                       \
-        first_axis_vec_kernel<Bytes, KK, false, true><<<(unsigned)blocks, 256, smem, stream>>>(   \
-            lab, f, nlines, (int)sx, table, border, flags, codes, (int)sy);                      \
-    } else {                                                                                     \
-      if (flags == 0)                                                                            \
-        first_axis_vec_kernel<Bytes, KK, true, false><<<(unsigned)blocks, 256, smem, stream>>>(   \
-            lab, f, nlines, (int)sx, table, border, flags, nullptr, 1);                          \
-      else                                                                                       \
-        first_axis_vec_kernel<Bytes, KK, false, false><<<(unsigned)blocks, 256, smem, stream>>>(  \
-            lab, f, nlines, (int)sx, table, border, flags, nullptr, 1);                          \
-    }                                                                                            \
-  } while (0)
-    if (sx <= 128)      EDT_LAUNCH_VEC(1);
-    else if (sx <= 256) EDT_LAUNCH_VEC(2);
-    else if (sx <= 512) EDT_LAUNCH_VEC(4);
-    else                EDT_LAUNCH_VEC(8);
-#undef EDT_LAUNCH_VEC
-    CUDA_TRY(cudaGetLastError());
-    if (codes_done) *codes_done = want_codes;
-    return 0;
-  }
-  const int nwords = (int)(sx >> 5) + 1;
-  const size_t per_warp = sizeof(uint32_t) * 4 * (size_t)nwords;
-  int warps = 8;
-  while (warps > 1 && per_warp * warps > (size_t)dc.max_smem_optin) warps >>= 1;
-  if (per_warp * warps > (size_t)dc.max_smem_optin) {
-    return fail(EDTB200_ELIMIT, "first axis of %lld voxels exceeds the shared-memory line buffer",
-                (long long)sx);
-  }
-  const size_t smem = per_warp * warps;
-  auto kern = first_axis_kernel<Bytes>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int64_t blocks = (nlines + warps - 1) / warps;
-  const int64_t cap = (int64_t)dc.sm_count * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  kern<<<(unsigned)blocks, warps * 32, smem, stream>>>(
-      static_cast<const typename LabelOf<Bytes>::type*>(labels), f, nlines, (int)sx, table, border, flags);
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-
-// Tensor map over the distance volume for one later-axis pass: dims (adjacent lines, line
-// length, outer), box = tx lines x box_rows.
-bool make_tile_map(CUtensorMap* map, float* f, const edtb200::LineGeom& g, int tx, int box_rows) {
-  EncodeTiledFn enc = tensor_map_encoder();
-  if (!enc) return false;
-  const cuuint64_t dims[3] = {(cuuint64_t)g.inner_count, (cuuint64_t)g.n, (cuuint64_t)g.outer_count};
-  const cuuint64_t strides[2] = {(cuuint64_t)g.line_stride * sizeof(float),
-                                 (cuuint64_t)(g.outer_count > 1 ? g.outer_stride : g.line_stride * (int64_t)g.n) *
-                                     sizeof(float)};
-  const cuuint32_t box[3] = {(cuuint32_t)tx, (cuuint32_t)box_rows, 1u};
-  const cuuint32_t estr[3] = {1u, 1u, 1u};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, f, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// Shared memory of one tile of `tx` lines (see later_axis_tile_kernel).
-size_t tile_smem_bytes(int n, int tx, int rows_alloc) {
-  const int nchunks = (n + 31) >> 5;
-  return (size_t)rows_alloc * tx * 4 + (size_t)nchunks * tx * 12 + (size_t)((n + 3) & ~1) * 4 + 16 +
-         (size_t)nchunks * tx;     // + one flag byte per (chunk, line)
-}
-
-template <int Bytes, int TX>
-int launch_tile(const void* labels, float* f, edtb200::LineGeom g, float w2, int border_lo, int border_hi,
-                int flags, bool use_tma, cudaStream_t stream, int code_bit = 0, bool pdl = false) {
-  using namespace edtb200;
-  using LT = typename LabelOf<Bytes>::type;
-  const int nchunks = (g.n + 31) >> 5;
-  TileBoxes tb;
-  tb.nboxes = (g.n + 255) / 256;
-  tb.box_rows = (g.n + tb.nboxes - 1) / tb.nboxes;
-  if (tb.nboxes > 1) tb.box_rows = (tb.box_rows + 3) & ~3;      // keeps every box 128-byte aligned
-  g.tiles_per_outer = (int)((g.inner_count + TX - 1) / TX);
-  const int64_t tiles = (int64_t)g.tiles_per_outer * g.outer_count;
-  if (tiles > 0x7fffffffLL) return fail(EDTB200_ELIMIT, "too many line tiles");
-  CUtensorMap map;
-  memset(&map, 0, sizeof(map));
-  if (use_tma && !make_tile_map(&map, f, g, TX, tb.box_rows)) use_tma = false;
-  const int rows_alloc = use_tma ? tb.box_rows * tb.nboxes : g.n;
-  const size_t smem = tile_smem_bytes(g.n, TX, rows_alloc);
-  constexpr int SUBS = 32 / TX;
-  int warps = (nchunks + SUBS - 1) / SUBS;
-  const bool wide = warps > 16;                 // long lines: one tile per SM, so give it 32 warps
-  if (warps > 32) warps = 32;
-  const LT* lab = static_cast<const LT*>(labels);
-  // Programmatic dependent launch: this pass may begin (label staging) while the previous pass of
-  // the stream drains its last wave; the kernel itself waits before touching the distances.
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)tiles);
-  cfg.blockDim = dim3((unsigned)(warps * 32));
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute pdl_attr[1];
-  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = pdl_attr;
-  static const bool pdl_off = getenv("EDTB200_NO_PDL") != nullptr;    // A/B switch for measurements
-  cfg.numAttrs = (pdl && !pdl_off) ? 1 : 0;   // only when the previous kernel of the stream is our own pass
-#define EDT_LAUNCH_TILE(EPI, TMA, CODES)                                                            \
-  do {                                                                                              \
-    if (wide) {                                                                                     \
-      auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, CODES, true>;                         \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, lab, f, g, tb, w2, border_lo, border_hi, flags, code_bit)); \
-    } else {                                                                                        \
-      auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, CODES, false>;                        \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, lab, f, g, tb, w2, border_lo, border_hi, flags, code_bit)); \
-    }                                                                                               \
-  } while (0)
-  if constexpr (Bytes == 1) {
-    if (code_bit) {
-      if (flags) { if (use_tma) EDT_LAUNCH_TILE(true, true, true); else EDT_LAUNCH_TILE(true, false, true); }
-      else       { if (use_tma) EDT_LAUNCH_TILE(false, true, true); else EDT_LAUNCH_TILE(false, false, true); }
-      CUDA_TRY(cudaGetLastError());
-      return 0;
-    }
-  }
-  if (flags) { if (use_tma) EDT_LAUNCH_TILE(true, true, false); else EDT_LAUNCH_TILE(true, false, false); }
-  else       { if (use_tma) EDT_LAUNCH_TILE(false, true, false); else EDT_LAUNCH_TILE(false, false, false); }
-#undef EDT_LAUNCH_TILE
-  CUDA_TRY(cudaGetLastError());
-  return 0;
-}
-
-// code_bit != 0: `labels` are the one-byte codes of the first-axis pass (Bytes must be 1); the
-// caller must have checked tile_path_ok() because only the tile kernel understands codes.
-template <int Bytes>
-int launch_later(const void* labels, float* f, const edtb200::LineGeom& g0, float w, int border_lo,
-                 int border_hi, int flags, const DeviceCache& dc, cudaStream_t stream, int code_bit = 0,
-                 bool pdl = false) {
-  using namespace edtb200;
-  using LT = typename LabelOf<Bytes>::type;
-  LineGeom g = g0;
-  const float w2 = w * w;                       // float product, as src/edt.hpp:181
-
-  // ---- shared-memory tile kernel: whole lines x TX adjacent lines per CTA ----
-  const bool fits32 = (int64_t)g.n * g.line_stride + 64 < (1LL << 32);
-  if (fits32 && g.n <= 4096 && g.inner_count < (1LL << 31)) {
-    const bool aligned = reinterpret_cast<uintptr_t>(f) % 16 == 0 && g.line_stride % 4 == 0 &&
-                         (g.outer_count <= 1 || g.outer_stride % 4 == 0);
-    // Tile width: 128-byte rows (TX = 32) keep DRAM pages and L2 lines whole and measured
-    // fastest even at one CTA per SM; narrower tiles only when a 32-wide tile cannot fit.
-    int tx = 0;
-    for (int cand = 32; cand >= 8 && !tx; cand >>= 1) {
-      const int nb = (g.n + 255) / 256;
-      int br = (g.n + nb - 1) / nb;
-      if (nb > 1) br = (br + 3) & ~3;
-      if (tile_smem_bytes(g.n, cand, br * nb) <= (size_t)dc.max_smem_optin) tx = cand;
-    }
-    if (tx) {
-      const bool use_tma = aligned && g.inner_count >= tx;
-      switch (tx) {
-        case 32: return launch_tile<Bytes, 32>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit, pdl);
-        case 16: return launch_tile<Bytes, 16>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit, pdl);
-        default: return launch_tile<Bytes, 8>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, code_bit, pdl);
-      }
-    }
-  }
-  if (code_bit) return fail(EDTB200_ELIMIT, "internal: neighbour codes need the tile kernel");
-  // ---- lines too long for a shared-memory tile: out of place through a temporary volume ----
-  const int64_t lines = g.inner_count * g.outer_count;
-  const size_t bytes = sizeof(float) * (size_t)lines * (size_t)g.n;
-  float* tmp = nullptr;
-  int* hull = nullptr;
-  CUDA_TRY(cudaMallocAsync(&tmp, bytes, stream));
-  if (cudaMallocAsync(&hull, bytes, stream) != cudaSuccess) {
-    cudaGetLastError();
-    cudaFreeAsync(tmp, stream);
-    return fail(EDTB200_ENOMEM, "no device memory for the long-line scratch volumes");
-  }
-  const int64_t blocks = (lines + 127) / 128;
-  if (blocks > 0x7fffffffLL) {
-    cudaFreeAsync(tmp, stream); cudaFreeAsync(hull, stream);
-    return fail(EDTB200_ELIMIT, "too many lines");
-  }
-  later_axis_long_kernel<Bytes><<<(unsigned)blocks, 128, 0, stream>>>(
-      static_cast<const LT*>(labels), f, tmp, hull, g, w2, border_lo, border_hi, flags);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(f, tmp, bytes, cudaMemcpyDeviceToDevice, stream));
-  CUDA_TRY(cudaFreeAsync(hull, stream));
-  CUDA_TRY(cudaFreeAsync(tmp, stream));
-  return 0;
-}
-
 int dispatch_first(int label_bytes, const void* labels, float* f, int64_t nlines, int64_t sx, float w,
-                   int border, int flags, DeviceCache& dc, cudaStream_t s, uint8_t* codes = nullptr,
-                   int64_t sy = 1, bool* codes_done = nullptr) {
+                   int border, int flags, DeviceCache& dc, cudaStream_t s) {
   switch (label_bytes) {
-    case 1: return launch_first<1>(labels, f, nlines, sx, w, border, flags, dc, s, codes, sy, codes_done);
-    case 2: return launch_first<2>(labels, f, nlines, sx, w, border, flags, dc, s, codes, sy, codes_done);
-    case 4: return launch_first<4>(labels, f, nlines, sx, w, border, flags, dc, s, codes, sy, codes_done);
-    default: return launch_first<8>(labels, f, nlines, sx, w, border, flags, dc, s, codes, sy, codes_done);
+    case 1: return launch_first<1>(labels, f, nlines, sx, w, border, flags, dc, s);
+    case 2: return launch_first<2>(labels, f, nlines, sx, w, border, flags, dc, s);
+    case 4: return launch_first<4>(labels, f, nlines, sx, w, border, flags, dc, s);
+    default: return launch_first<8>(labels, f, nlines, sx, w, border, flags, dc, s);
   }
-}
-
-// Will launch_later() take the shared-memory tile kernel for this geometry?  (same conditions)
-bool tile_path_ok(const edtb200::LineGeom& g, const DeviceCache& dc) {
-  if (!((int64_t)g.n * g.line_stride + 64 < (1LL << 32) && g.n <= 4096 && g.inner_count < (1LL << 31))) return false;
-  const int nb = (g.n + 255) / 256;
-  int br = (g.n + nb - 1) / nb;
-  if (nb > 1) br = (br + 3) & ~3;
-  return tile_smem_bytes(g.n, 8, br * nb) <= (size_t)dc.max_smem_optin;
 }
 
 int dispatch_later(int label_bytes, const void* labels, float* f, const edtb200::LineGeom& g, float w,
-                   int lo, int hi, int flags, const DeviceCache& dc, cudaStream_t s, int code_bit = 0,
-                   bool pdl = false) {
+                   int lo, int hi, int flags, DeviceCache& dc, cudaStream_t s, bool pdl = false) {
   switch (label_bytes) {
-    case 1: return launch_later<1>(labels, f, g, w, lo, hi, flags, dc, s, code_bit, pdl);
-    case 2: return launch_later<2>(labels, f, g, w, lo, hi, flags, dc, s, code_bit, pdl);
-    case 4: return launch_later<4>(labels, f, g, w, lo, hi, flags, dc, s, code_bit, pdl);
-    default: return launch_later<8>(labels, f, g, w, lo, hi, flags, dc, s, code_bit, pdl);
+    case 1: return launch_later<1>(labels, f, g, w, lo, hi, flags, dc, s, pdl);
+    case 2: return launch_later<2>(labels, f, g, w, lo, hi, flags, dc, s, pdl);
+    case 4: return launch_later<4>(labels, f, g, w, lo, hi, flags, dc, s, pdl);
+    default: return launch_later<8>(labels, f, g, w, lo, hi, flags, dc, s, pdl);
   }
 }
 
@@ -618,40 +421,28 @@ int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_
   // changes the first pass only -- later passes treat every run alike.
   const int epilogue = ((flags & EDTB200_SQRT) ? kSqrt : 0) | ((flags & EDTB200_SIGNED) ? kNegate : 0);
   const int zero_label = (flags & EDTB200_SIGNED) ? kZeroLabel : 0;
-  // EXPERIMENT, off by default (EDTB200_USE_CODES=1 turns it on): read labels wider than one byte
-  // ONCE -- the first-axis pass leaves a one-byte code per voxel (differs from its y / z
-  // neighbour, is background) and the later passes read that instead (3L+20 -> L+22 bytes per
-  // voxel of HBM traffic).  Measured on B200, 512^3 uint32: Y 0.261 -> 0.244 ms, Z 0.280 -> 0.250 ms,
-  // but the first-axis pass 0.180 -> 0.350 ms (two more label rows through L2 + 75 registers), a
-  // net loss (0.84 vs 0.73 ms), so the passes read the labels by default.
   // The later passes are launched with programmatic stream serialization: the kernel before them
   // in the stream is our own previous pass, which never writes the labels, so their label staging
   // (before griddepcontrol.wait) may overlap its tail.  The per-axis entry points do not do this:
   // there the previous kernel is the caller's and may be the one producing the labels.
+  // (A one-byte neighbour-code plane written by the first pass, so that the later passes need not
+  // re-read wide labels, was measured in round 1 and dropped: Y 0.261 -> 0.244, Z 0.280 -> 0.250 ms
+  // but X 0.180 -> 0.350 ms at 512^3 uint32.)
   int rc = 0;
-  uint8_t* codes = nullptr;
-  bool codes_done = false;
   const edtb200::LineGeom gy = geom_for_axis(1, sx, sy, sz), gz = geom_for_axis(2, sx, sy, sz);
-  static const bool codes_enabled = getenv("EDTB200_USE_CODES") != nullptr;
-  if (codes_enabled && label_bytes > 1 && ndim >= 2 && tile_path_ok(gy, dc) && (ndim < 3 || tile_path_ok(gz, dc)))
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&codes), (size_t)(sx * sy * sz), stream));
   mark_pass(0, stream);
   rc = dispatch_first(label_bytes, labels, f, sy * sz, sx, wx, border, zero_label | (ndim == 1 ? epilogue : 0), dc,
-                      stream, codes, sy, &codes_done);
+                      stream);
   mark_pass(1, stream);
   if (!rc && ndim >= 2) {
-    rc = codes_done ? dispatch_later(1, codes, f, gy, wy, border, border, ndim == 2 ? epilogue : 0, dc, stream, 1)
-                    : dispatch_later(label_bytes, labels, f, gy, wy, border, border, ndim == 2 ? epilogue : 0, dc,
-                                     stream, 0, /*pdl=*/true);
+    rc = dispatch_later(label_bytes, labels, f, gy, wy, border, border, ndim == 2 ? epilogue : 0, dc, stream,
+                        /*pdl=*/true);
     mark_pass(2, stream);
   }
   if (!rc && ndim >= 3) {
-    rc = codes_done ? dispatch_later(1, codes, f, gz, wz, border, border, epilogue, dc, stream, 2)
-                    : dispatch_later(label_bytes, labels, f, gz, wz, border, border, epilogue, dc, stream, 0,
-                                     /*pdl=*/true);
+    rc = dispatch_later(label_bytes, labels, f, gz, wz, border, border, epilogue, dc, stream, /*pdl=*/true);
     mark_pass(3, stream);
   }
-  if (codes) cudaFreeAsync(codes, stream);
   return rc;
 }
 
@@ -679,7 +470,6 @@ int edtb200_transform(const void* labels, int label_bytes, int ndim, int64_t sx,
   if (total == 0) return 0;
   if (!labels || !out) return fail(EDTB200_EINVAL, "null pointer");
 
-  std::lock_guard<std::mutex> lock(g_mutex);
   DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
@@ -690,11 +480,17 @@ int edtb200_transform(const void* labels, int label_bytes, int ndim, int64_t sx,
   const int border = black_border != 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
 
+  // device-resident: asynchronous on the caller's stream, no library-wide or per-device lock held
   if (lab_dev && out_dev)
     return run_passes(labels, label_bytes, ndim, sx, sy, sz, wx, wy, wz, border, flags, out, *dc, stream);
 
-  // host memory involved: stage through cached device buffers, synchronous on return
-  if (!stream) {
+  // host memory involved: stage through this device's cached buffers, synchronous on return.
+  // Calls on other devices proceed concurrently (per-device lock).
+  std::lock_guard<std::mutex> host_call(dc->host_call);
+  if (!stream && !lab_dev && !out_dev) {
+    // pure host call: a private non-blocking stream.  With one side on the device and no stream
+    // given, the legacy default stream (NULL) is kept: it is ordered after the work the caller
+    // queued on the default / blocking streams that produced that buffer.
     if (!dc->stream) CUDA_TRY(cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking));
     stream = dc->stream;
   }
@@ -747,12 +543,12 @@ int edtb200_transform_batch(const void* const* labels, float* const* outs, int c
   for (int k = 0; k < count; ++k)
     if (!labels[k] || !outs[k]) return fail(EDTB200_EINVAL, "null pointer in volume %d", k);
 
-  std::lock_guard<std::mutex> lock(g_mutex);
   DeviceGuard restore_device;
   DeviceCache* dcp = nullptr;
   rc = probe(device, &dcp);
   if (rc) return rc;
   DeviceCache& dc = *dcp;
+  std::lock_guard<std::mutex> host_call(dc.host_call);
   const size_t lab_bytes = (size_t)total * (size_t)label_bytes, out_bytes = (size_t)total * sizeof(float);
   auto grow = [](void** p, size_t* have, size_t need) -> cudaError_t {
     if (*have >= need) return cudaSuccess;
@@ -870,7 +666,6 @@ int edtb200_transform_voxel_graph(const void* labels, int label_bytes, const uns
   if (rc) return rc;
   const int64_t total2 = sx2 * sy2 * sz2;
 
-  std::lock_guard<std::mutex> lock(g_mutex);
   DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
@@ -878,7 +673,9 @@ int edtb200_transform_voxel_graph(const void* labels, int label_bytes, const uns
   const bool in_dev = flags & EDTB200_LABELS_ON_DEVICE;
   const bool out_dev = flags & EDTB200_OUT_ON_DEVICE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!stream && !(in_dev && out_dev)) {
+  std::unique_lock<std::mutex> host_call(dc->host_call, std::defer_lock);
+  if (!(in_dev && out_dev)) host_call.lock();          // staging buffers and the private stream
+  if (!stream && !in_dev && !out_dev) {
     if (!dc->stream) CUDA_TRY(cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking));
     stream = dc->stream;
   }
@@ -896,19 +693,19 @@ int edtb200_transform_voxel_graph(const void* labels, int label_bytes, const uns
   const void* lab = labels;
   const uint8_t* gr = graph;
   if (!in_dev) {
-    VG_TRY(cudaMallocAsync(&d_labels, (size_t)total * label_bytes, stream));
-    VG_TRY(cudaMallocAsync(&d_graph, (size_t)total, stream));
+    VG_TRY(scratch_alloc(*dc, &d_labels, (size_t)total * label_bytes, stream));
+    VG_TRY(scratch_alloc(*dc, &d_graph, (size_t)total, stream));
     rc = upload(d_labels, labels, (size_t)total * label_bytes, device, stream);
     if (!rc) rc = upload(d_graph, graph, (size_t)total, device, stream);
     if (rc) { release(); return rc; }
     lab = d_labels;
     gr = static_cast<const uint8_t*>(d_graph);
   }
-  VG_TRY(cudaMallocAsync(&d_cells, (size_t)total2, stream));
-  VG_TRY(cudaMallocAsync(&d_doubled, (size_t)total2 * sizeof(float), stream));
+  VG_TRY(scratch_alloc(*dc, &d_cells, (size_t)total2, stream));
+  VG_TRY(scratch_alloc(*dc, &d_doubled, (size_t)total2 * sizeof(float), stream));
   float* result = out;
   if (!out_dev) {
-    VG_TRY(cudaMallocAsync(&d_result, (size_t)total * sizeof(float), stream));
+    VG_TRY(scratch_alloc(*dc, &d_result, (size_t)total * sizeof(float), stream));
     result = static_cast<float*>(d_result);
   }
 
@@ -946,7 +743,6 @@ int edtb200_pass_first(const void* labels_dev, int label_bytes, int64_t sx, int6
   if (rc) return rc;
   if (sx * sy * sz == 0) return 0;
   if (!labels_dev || !f_dev) return fail(EDTB200_EINVAL, "null pointer");
-  std::lock_guard<std::mutex> lock(g_mutex);
   DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
@@ -965,7 +761,6 @@ int edtb200_pass_later(const void* labels_dev, int label_bytes, int axis, int64_
   if (axis != 1 && axis != 2) return fail(EDTB200_EINVAL, "axis must be 1 (Y) or 2 (Z)");
   if (sx * sy * sz == 0) return 0;
   if (!labels_dev || !f_dev) return fail(EDTB200_EINVAL, "null pointer");
-  std::lock_guard<std::mutex> lock(g_mutex);
   DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
@@ -985,7 +780,6 @@ int edtb200_slab_face_runs(const void* labels_dev, int label_bytes, int64_t sx, 
   if (halo < 1 || halo > 254) return fail(EDTB200_EINVAL, "halo must be in 1..254");
   if (sx * sy * sz == 0) return 0;
   if (!labels_dev || !m_dev || !overflow_dev) return fail(EDTB200_EINVAL, "null pointer");
-  std::lock_guard<std::mutex> lock(g_mutex);
   DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
@@ -1014,7 +808,6 @@ int edtb200_slab_face_fixup(const void* labels_dev, int label_bytes, int64_t sx,
   if (halo < 1 || halo > 254) return fail(EDTB200_EINVAL, "halo must be in 1..254");
   if (sx * sy * sz == 0) return 0;
   if (!labels_dev || !nb_label_dev || !nb_m_dev || !nb_f_dev || !f_dev) return fail(EDTB200_EINVAL, "null pointer");
-  std::lock_guard<std::mutex> lock(g_mutex);
   DeviceGuard restore_device;
   DeviceCache* dc = nullptr;
   rc = probe(device, &dc);
@@ -1056,18 +849,22 @@ int edtb200_pass_ms(int steps_back, float* ms3) {
 }
 
 int edtb200_release(void) {
-  std::lock_guard<std::mutex> lock(g_mutex);
   DeviceGuard restore_device;
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
   for (int d = 0; d < count && d < kMaxDevices; ++d) {
     DeviceCache& dc = g_cache[d];
-    bool any = dc.labels || dc.dist || dc.stream || dc.labels2 || dc.dist2 || dc.stream_up;
-    for (auto& t : dc.tables) any = any || t.data;
-    if (!any) continue;
+    std::lock_guard<std::mutex> host_call(dc.host_call);
+    std::lock_guard<std::mutex> guard(dc.lock);
+    if (!dc.probed) continue;
     cudaSetDevice(d);
     cudaDeviceSynchronize();
-    for (auto& t : dc.tables) { if (t.data) cudaFree(t.data); if (t.ready) cudaEventDestroy(t.ready); }
+    for (auto& t : dc.tables) {
+      if (t.data) cudaFree(t.data);
+      if (t.ready) cudaEventDestroy(t.ready);
+      for (auto& e : t.used) if (e) cudaEventDestroy(e);
+      t = DeviceCache::Table();
+    }
     if (dc.stream) { cudaStreamSynchronize(dc.stream); cudaStreamDestroy(dc.stream); }
     if (dc.labels) cudaFree(dc.labels);
     if (dc.dist) cudaFree(dc.dist);
@@ -1080,16 +877,21 @@ int edtb200_release(void) {
       if (dc.ev_comp[i]) cudaEventDestroy(dc.ev_comp[i]);
       if (dc.ev_down[i]) cudaEventDestroy(dc.ev_down[i]);
     }
-    dc = DeviceCache();
-  }
-  for (int dir = 0; dir < 2; ++dir)
-    for (int d = 0; d < count && d < kMaxDevices; ++d) {
+    dc.labels = dc.labels2 = nullptr; dc.dist = dc.dist2 = nullptr;
+    dc.labels_bytes = dc.labels2_bytes = dc.dist_bytes = dc.dist2_bytes = 0;
+    dc.stream = dc.stream_up = dc.stream_down = nullptr;
+    for (int i = 0; i < 2; ++i) dc.ev_up[i] = dc.ev_comp[i] = dc.ev_down[i] = nullptr;
+    // everything the stream-ordered scratch pool still holds goes back to the driver
+    if (dc.pool) cudaMemPoolTrimTo(dc.pool, 0);
+    for (int dir = 0; dir < 2; ++dir) {
       StageBuffers& sb = g_stage[dir][d];
       for (int i = 0; i < kStages; ++i) {
         if (sb.buf[i]) { cudaFreeHost(sb.buf[i]); sb.buf[i] = nullptr; }
         if (sb.ev[i]) { cudaEventDestroy(sb.ev[i]); sb.ev[i] = nullptr; }
       }
     }
+    cudaGetLastError();
+  }
   return 0;
 }
 

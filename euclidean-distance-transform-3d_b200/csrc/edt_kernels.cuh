@@ -56,7 +56,7 @@ __device__ __forceinline__ float finish_value(float v, bool background, int flag
 
 // T[k] for k = 0..count-1 (see header).  One thread: the adds are sequential by definition
 // (src/edt.hpp:92-118 accumulates d[i] = d[i-1] + w in float32).
-__global__ void step_table_kernel(float w, int count, float* __restrict__ table) {
+static __global__ void step_table_kernel(float w, int count, float* __restrict__ table) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   float a = 0.0f;
   table[0] = 0.0f;
@@ -229,17 +229,11 @@ template <> struct Vec4Labels<8> {
 
 // Plain = true: squared EDT, background forced to 0, no sqrt / sign (the hot configuration);
 // Plain = false: behaviour selected by `flags` at run time.
-// Codes = true: additionally emit one byte per voxel for the later-axis passes, so that they
-// need not read the (wider) labels again:  bit 0 = label differs from (x, y-1, z),
-// bit 1 = label differs from (x, y, z-1), bit 2 = label is background.  The two neighbour rows
-// were read moments ago by neighbouring warps (row y-1) / the previous slice (z-1, 1 MiB back
-// at 512^2), i.e. they come from L1/L2, not from HBM.
-template <int Bytes, int K, bool Plain, bool Codes>
+template <int Bytes, int K, bool Plain>
 __global__ void __launch_bounds__(256)
 first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
                       float* __restrict__ out, int64_t nlines, int sx,
-                      const float* __restrict__ table, int border, int flags,
-                      uint8_t* __restrict__ codes, int sy) {
+                      const float* __restrict__ table, int border, int flags) {
   using LT = typename LabelOf<Bytes>::type;
   using WT = typename LabelOf<Bytes>::wide;
   extern __shared__ float table_s[];                 // T[0..sx], then +inf at sx + 1
@@ -293,30 +287,6 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
       occ[b] = __ballot_sync(full, m != 0);
       edges |= m << (4 * b);
       zeros |= z << (4 * b);
-    }
-
-    if (Codes) {
-      const int64_t zi = line / sy;
-      const int yi = (int)(line - zi * sy);
-      uint8_t* __restrict__ crow = codes + line * sx;
-#pragma unroll
-      for (int b = 0; b < K; ++b) {
-        const int q0 = (b << 7) + (lane << 2);
-        if (q0 >= sx) continue;
-        WT up[4], dn[4];
-        if (yi > 0) Vec4Labels<Bytes>::load(src - sx + q0, up);
-        if (zi > 0) Vec4Labels<Bytes>::load(src - (int64_t)sx * sy + q0, dn);
-        uint32_t packed = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          uint32_t cde = 0;
-          if (yi > 0 && up[e] != v[b][e]) cde |= 1u;
-          if (zi > 0 && dn[e] != v[b][e]) cde |= 2u;
-          if (v[b][e] == 0) cde |= 4u;
-          packed |= cde << (8 * e);
-        }
-        *reinterpret_cast<uint32_t*>(crow + q0) = packed;
-      }
     }
 
     // ---- nearest boundary strictly below / above the lane's 4 voxels, per block ----
@@ -562,105 +532,9 @@ __device__ __forceinline__ int next_vertex(const TileLine<TX> ln, int pos, int b
   }
 }
 
-// Write the outputs of rows [lo, hi) of the run [a, b) by walking the (final) hull of the run.
-//   sq = shared address of the border-term table; line0 = byte address of row 0 in global memory.
-template <int TX, bool Epilogue>
-__device__ __forceinline__ void read_out(const TileLine<TX> ln, int lo, int hi, int a, int b, float w2f,
-                                         bool lo_border, bool hi_border, uint32_t sq,
-                                         char* __restrict__ line0, size_t pitch, bool background, int flags) {
-  const float inf = __int_as_float(0x7f800000);
-  // vertex that dominates row `lo`: start at the nearest vertex at or below lo (else the first one
-  // above), then descend along the hull -- at a fixed row the candidate values are unimodal.
-  int v = prev_vertex<TX>(ln, lo + 1, a);
-  if (v < 0) v = next_vertex<TX>(ln, lo, b);
-  float fv = inf, dv = 0.0f;
-  if (v >= 0) {
-    fv = ln.fval(v);
-    dv = (float)(lo - v);
-    float best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
-    for (;;) {
-      const int u = prev_vertex<TX>(ln, v, a);
-      if (u < 0) break;
-      const float fu = ln.fval(u);
-      const float du = (float)(lo - u);
-      const float cand = __fmaf_rn(w2f, __fmul_rn(du, du), fu);
-      if (!(cand < best)) break;
-      best = cand; v = u; fv = fu; dv = du;
-    }
-  }
-  int v1 = (v >= 0) ? next_vertex<TX>(ln, v, b) : -1;
-  float fv1 = inf, dv1 = 0.0f;
-  if (v1 >= 0) { fv1 = ln.fval(v1); dv1 = (float)(lo - v1); }
-  char* dst = line0 + (size_t)lo * pitch;
-  uint32_t sq_lo = sq + (uint32_t)(lo - a + 1) * 4u;     // sq[i - a + 1]
-  uint32_t sq_hi = sq + (uint32_t)(b - lo) * 4u;         // sq[b - i]
-  for (int i = lo; i < hi; ++i) {
-    float best = inf;
-    if (v >= 0) {
-      best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
-      while (v1 >= 0) {
-        const float cand = __fmaf_rn(w2f, __fmul_rn(dv1, dv1), fv1);
-        if (!(cand <= best)) break;
-        best = cand; v = v1; fv = fv1; dv = dv1;
-        v1 = next_vertex<TX>(ln, v1, b);
-        if (v1 >= 0) { fv1 = ln.fval(v1); dv1 = (float)(i - v1); }
-      }
-      dv += 1.0f; dv1 += 1.0f;
-    }
-    if (lo_border) best = fminf(best, lds_f32(sq_lo));
-    if (hi_border) best = fminf(best, lds_f32(sq_hi));
-    sq_lo += 4u; sq_hi -= 4u;
-    if (Epilogue) best = finish_value(best, background, flags);   // a run has one label
-    *reinterpret_cast<float*>(dst) = best;
-    dst += pitch;
-  }
-}
-
-// Same for a run [sa, sb) that lies inside one 32-row chunk starting at row i0: the hull is the
-// register word `hb` (bit = row - i0), so navigation is a handful of bit operations.
-template <int TX, bool Epilogue>
-__device__ __forceinline__ void read_out_local(const TileLine<TX> ln, uint32_t hb, int i0, int sa, int sb,
-                                               float w2f, bool lo_border, bool hi_border, uint32_t sq,
-                                               char* __restrict__ line0, size_t pitch, bool background,
-                                               int flags) {
-  const float inf = __int_as_float(0x7f800000);
-  uint32_t left = hb & (0xffffffffu << (sa - i0));       // vertices of this run, bits relative to i0
-  if (sb - i0 < 32) left &= (1u << (sb - i0)) - 1u;
-  int v = -1, v1 = -1;
-  float fv = inf, fv1 = inf, dv = 0.0f, dv1 = 0.0f;
-  if (left) {
-    v = i0 + __ffs(left) - 1; left &= left - 1u;
-    fv = ln.fval(v); dv = (float)(sa - v);
-    if (left) { v1 = i0 + __ffs(left) - 1; left &= left - 1u; fv1 = ln.fval(v1); dv1 = (float)(sa - v1); }
-  }
-  char* dst = line0 + (size_t)sa * pitch;
-  uint32_t sq_lo = sq + 4u;                              // sq[i - sa + 1]
-  uint32_t sq_hi = sq + (uint32_t)(sb - sa) * 4u;        // sq[sb - i]
-  for (int i = sa; i < sb; ++i) {
-    float best = inf;
-    if (v >= 0) {
-      best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
-      while (v1 >= 0) {
-        const float cand = __fmaf_rn(w2f, __fmul_rn(dv1, dv1), fv1);
-        if (!(cand <= best)) break;
-        best = cand; v = v1; fv = fv1; dv = dv1;
-        if (left) { v1 = i0 + __ffs(left) - 1; left &= left - 1u; fv1 = ln.fval(v1); dv1 = (float)(i - v1); }
-        else v1 = -1;
-      }
-      dv += 1.0f; dv1 += 1.0f;
-    }
-    if (lo_border) best = fminf(best, lds_f32(sq_lo));
-    if (hi_border) best = fminf(best, lds_f32(sq_hi));
-    sq_lo += 4u; sq_hi -= 4u;
-    if (Epilogue) best = finish_value(best, background, flags);
-    *reinterpret_cast<float*>(dst) = best;
-    dst += pitch;
-  }
-}
-
-// A long run [a, b) (more than 32 rows, so it spans chunk boundaries) is constant if each of its
-// chunk segments was found constant in stage 1 (flag bits, see the kernel) and all segments
-// share one value.  Then no scan is needed at all: out = min(f, border terms).
+// A run [a, b) that crosses chunk boundaries is constant if each of its chunk segments was found
+// constant in stage 1 (flag bits, see the kernel) and all segments share one value.  Then no scan
+// is needed at all: out = min(f, border terms).
 template <int TX>
 __device__ __forceinline__ bool run_is_constant(const TileLine<TX> ln, uint32_t cflagcol, int a, int b) {
   const int ca = a >> 5, cb = (b - 1) >> 5;
@@ -673,76 +547,56 @@ __device__ __forceinline__ bool run_is_constant(const TileLine<TX> ln, uint32_t 
   return true;
 }
 
-template <int TX, bool Epilogue>
-__device__ __forceinline__ void write_constant_run(const TileLine<TX> ln, int lo, int hi, int a, int b,
-                                                   bool lo_border, bool hi_border, uint32_t sq,
-                                                   char* __restrict__ line0, size_t pitch, bool background,
-                                                   int flags) {
-  const float f0 = ln.fval(a);
-  char* dst = line0 + (size_t)lo * pitch;
-  uint32_t sq_lo = sq + (uint32_t)(lo - a + 1) * 4u;     // sq[i - a + 1]
-  uint32_t sq_hi = sq + (uint32_t)(b - lo) * 4u;         // sq[b - i]
-  for (int i = lo; i < hi; ++i) {
-    float best = f0;
-    if (lo_border) best = fminf(best, lds_f32(sq_lo));
-    if (hi_border) best = fminf(best, lds_f32(sq_hi));
-    sq_lo += 4u; sq_hi -= 4u;
-    if (Epilogue) best = finish_value(best, background, flags);
-    *reinterpret_cast<float*>(dst) = best;
-    dst += pitch;
-  }
+// Rows of the chunk (bit = row - i0) that belong to a NON-constant segment.  `starts` has a bit at
+// the first row of every segment (bit 0 always), `breaks` a bit at every row whose sample differs
+// from the row below it inside a segment.  Every break bit is spread over its whole segment: up to
+// the segment's last row by letting a carry ripple through the ones of ~starts, and down to its
+// first row by the same trick on the bit-reversed words.
+__device__ __forceinline__ uint32_t nonconstant_rows(uint32_t starts, uint32_t breaks) {
+  const uint32_t m = ~starts;
+  const uint32_t up = (((m + breaks) ^ m) | breaks) & m;                  // break row .. last row of the segment
+  const uint32_t mr = ~__brev((starts >> 1) | 0x80000000u);              // zeros at the segments' last rows
+  const uint32_t br = __brev(breaks >> 1);                               // the row below each break
+  const uint32_t down = (((mr + br) ^ mr) | br) & mr;                    // first row of the segment .. row below the break
+  return up | __brev(down);
 }
 
-// True if every sample of rows [sa, sb) equals the first one (returned in f0).  Equal-height
-// parabolas never hide one another, so a constant segment needs no envelope scan at all: every
-// row is its own best site and its value is min(f0, border terms).  This is the common case
-// inside blocky segmentations and inside large binary objects along the later axes.
+// Lower envelopes of all the segments marked in `todo` (bit = row - i0; whole segments, each one
+// beginning at a bit of `starts`), as vertex bits added to `hb`.  One loop over the marked rows for
+// every lane, whatever the number and the lengths of the segments in its chunk: the vertex stack
+// simply restarts where a segment starts.  Classic stack scan with the stack kept as bits: top
+// vertex q, the one below it p, and (num, den) = numerator / denominator of s(p,q) so that each
+// test is a cross-multiplication in double; samples of +inf are not sites.
 template <int TX>
-__device__ __forceinline__ bool segment_constant(const TileLine<TX> ln, int sa, int sb, float& f0) {
-  uint32_t at = ln.f + (uint32_t)sa * TileLine<TX>::ROW;
-  f0 = lds_f32(at);
-  bool same = true;
-  for (int r = sa + 1; r < sb; ++r) {
-    at += TileLine<TX>::ROW;
-    same = same && (lds_f32(at) == f0);
-  }
-  return same;
-}
-
-// Lower envelope of the finite samples of rows [sa, sb) (sb - o <= 32), as a bit mask relative
-// to row `o`: returns hb with the bits of the surviving vertices set (other bits untouched).
-// Classic stack scan with the stack kept as bits: top vertex q, the one below it p, and
-// (num, den) = numerator / denominator of s(p,q) so that each test is a cross-multiplication.
-template <int TX>
-__device__ __forceinline__ uint32_t build_hull(const TileLine<TX> ln, int o, int sa, int sb, double w2d,
-                                               uint32_t hb) {
+__device__ __forceinline__ uint32_t build_hull_rows(const TileLine<TX> ln, int i0, uint32_t todo, uint32_t starts,
+                                                    double w2d, uint32_t hb) {
   const float inf = __int_as_float(0x7f800000);
-  const uint32_t segmask = 0xffffffffu << (sa - o);
-  int cnt = 0, q = 0, p = 0;
+  int cnt = 0, q = 0, p = 0;                                  // rows relative to i0
   double qd = 0.0, fqd = 0.0, num = 0.0, den = 1.0;
-  double rd = (double)sa;
-  uint32_t fr_a = ln.f + (uint32_t)sa * TileLine<TX>::ROW;
-  for (int r = sa; r < sb; ++r, rd += 1.0, fr_a += TileLine<TX>::ROW) {
-    const float fr = lds_f32(fr_a);
-    if (!(fr < inf)) continue;                       // +inf: not a site
-    const double frd = (double)fr;
+  uint32_t segmask = 0xffffffffu;
+  for (uint32_t rest = todo; rest; rest &= rest - 1u) {
+    const int r = __ffs(rest) - 1;
+    if ((starts >> r) & 1u) { cnt = 0; segmask = 0xffffffffu << r; }
+    const float fr = ln.fval(i0 + r);
+    if (!(fr < inf)) continue;                                // +inf: not a site
+    const double frd = (double)fr, rd = (double)(i0 + r);
     double den_r = rd - qd;
     double num_r = (frd - fqd) + w2d * (den_r * (rd + qd));
-    while (cnt >= 2 && num_r * den <= num * den_r) {  // s(q,r) <= s(p,q): q is hidden
-      hb &= ~(1u << (q - o));
+    while (cnt >= 2 && num_r * den <= num * den_r) {          // s(q,r) <= s(p,q): q is hidden
+      hb &= ~(1u << q);
       --cnt;
-      q = p; qd = (double)q; fqd = (double)ln.fval(q);
+      q = p; qd = (double)(i0 + q); fqd = (double)ln.fval(i0 + q);
       if (cnt >= 2) {
-        const uint32_t m = hb & segmask & ((1u << (q - o)) - 1u);
-        p = o + 31 - __clz(m);
-        const double pd = (double)p;
+        const uint32_t m = hb & segmask & ((1u << q) - 1u);
+        p = 31 - __clz(m);
+        const double pd = (double)(i0 + p);
         den = qd - pd;
-        num = (fqd - (double)ln.fval(p)) + w2d * (den * (qd + pd));
+        num = (fqd - (double)ln.fval(i0 + p)) + w2d * (den * (qd + pd));
       }
       den_r = rd - qd;
       num_r = (frd - fqd) + w2d * (den_r * (rd + qd));
     }
-    hb |= 1u << (r - o);
+    hb |= 1u << r;
     ++cnt;
     p = q; num = num_r; den = den_r;
     q = r; qd = rd; fqd = frd;
@@ -750,16 +604,109 @@ __device__ __forceinline__ uint32_t build_hull(const TileLine<TX> ln, int o, int
   return hb;
 }
 
-// FromCodes = true: `labels` holds the one-byte codes written by first_axis_vec_kernel<..., Codes>
-// (Bytes = 1) and `code_bit` selects the axis (1 = y neighbour, 2 = z neighbour).
-// Wide = false: up to 16 warps per CTA, register budget for 3 CTAs per SM (lines <= 512 voxels fit
-// three tiles per SM).  Wide = true: up to 32 warps for long lines, whose tile fills an SM alone.
-template <int Bytes, int TX, bool Epilogue, bool UseTMA, bool FromCodes, bool Wide>
+// Outputs of the rows in `todo` (bit = row - i0): rows of runs that lie INSIDE the chunk (first
+// row at a bit of `starts`, last row at a bit of `ends`).  One loop over the marked rows for every
+// lane; a run's state is set up at its first row.  A run whose rows are not marked in `noncst` is
+// constant: every row is its own best site.  Otherwise the hull bits of the run in `hb` are walked
+// (candidate values along the hull are unimodal at a fixed row) and each candidate is evaluated
+// with one fused multiply-add, the correctly rounded w2*d^2 + f[v] of src/edt.hpp:225-230.
+template <int TX, bool Epilogue>
+__device__ __forceinline__ void read_out_rows_local(const TileLine<TX> ln, int i0, uint32_t todo, uint32_t starts,
+                                                    uint32_t ends, uint32_t noncst, uint32_t hb, uint32_t wzero,
+                                                    int n, float w2f, bool border_lo, bool border_hi, uint32_t sq,
+                                                    char* __restrict__ line0, size_t pitch, int flags) {
+  const float inf = __int_as_float(0x7f800000);
+  int a = 0, b = 0, v = -1, v1 = -1;
+  bool lo_b = false, hi_b = false, cst = true, bg = false;
+  uint32_t left = 0u;
+  float fv = inf, fv1 = inf, dv = 0.0f, dv1 = 0.0f;
+  for (uint32_t rest = todo; rest; rest &= rest - 1u) {
+    const int r = __ffs(rest) - 1;
+    const int i = i0 + r;
+    if ((starts >> r) & 1u) {                                 // first row of a run
+      const int e = __ffs(ends & (0xffffffffu << r)) - 1;     // its last row
+      a = i; b = i0 + e + 1;
+      lo_b = a > 0 || border_lo; hi_b = b < n || border_hi;
+      cst = !((noncst >> r) & 1u);
+      bg = (wzero >> r) & 1u;
+      v = v1 = -1; fv = fv1 = inf;
+      if (!cst) {
+        left = hb & (0xffffffffu << r) & (0xffffffffu >> (31 - e));
+        if (left) {
+          v = __ffs(left) - 1; left &= left - 1u;
+          fv = ln.fval(i0 + v); dv = (float)(r - v);
+          if (left) { v1 = __ffs(left) - 1; left &= left - 1u; fv1 = ln.fval(i0 + v1); dv1 = (float)(r - v1); }
+        }
+      }
+    }
+    float best = inf;
+    if (cst) {
+      best = ln.fval(i);
+    } else if (v >= 0) {
+      best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
+      while (v1 >= 0) {
+        const float cand = __fmaf_rn(w2f, __fmul_rn(dv1, dv1), fv1);
+        if (!(cand <= best)) break;
+        best = cand; v = v1; fv = fv1; dv = dv1;
+        if (left) { v1 = __ffs(left) - 1; left &= left - 1u; fv1 = ln.fval(i0 + v1); dv1 = (float)(r - v1); }
+        else v1 = -1;
+      }
+      dv += 1.0f; dv1 += 1.0f;
+    }
+    if (lo_b) best = fminf(best, lds_f32(sq + (uint32_t)(i - a + 1) * 4u));
+    if (hi_b) best = fminf(best, lds_f32(sq + (uint32_t)(b - i) * 4u));
+    if (Epilogue) best = finish_value(best, bg, flags);       // a run has one label
+    *reinterpret_cast<float*>(line0 + (size_t)i * pitch) = best;
+  }
+}
+
+// State of the walk along the final hull of a run [a, b) that crosses chunk boundaries, for the
+// rows of one chunk; see read_out_rows_crossing.
+struct HullWalk {
+  int a, b, v, v1;
+  float fv, fv1, dv, dv1;
+  bool lo_b, hi_b, cst, bg;
+};
+
+// Sets the walk up for row `lo` of the run [a, b): the vertex that dominates row lo is found by
+// starting at the nearest vertex at or below lo (else the first one above) and descending along
+// the hull -- at a fixed row the candidate values are unimodal.
+template <int TX>
+__device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, uint32_t cflagcol, int lo, int a, int b,
+                                           int n, float w2f, bool border_lo, bool border_hi, bool background) {
+  const float inf = __int_as_float(0x7f800000);
+  w.a = a; w.b = b;
+  w.lo_b = a > 0 || border_lo; w.hi_b = b < n || border_hi;
+  w.bg = background;
+  w.cst = run_is_constant<TX>(ln, cflagcol, a, b);
+  w.v = w.v1 = -1; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
+  if (w.cst) return;
+  int v = prev_vertex<TX>(ln, lo + 1, a);
+  if (v < 0) v = next_vertex<TX>(ln, lo, b);
+  if (v >= 0) {
+    float fv = ln.fval(v), dv = (float)(lo - v);
+    float best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
+    for (;;) {
+      const int u = prev_vertex<TX>(ln, v, a);
+      if (u < 0) break;
+      const float fu = ln.fval(u);
+      const float du = (float)(lo - u);
+      const float cand = __fmaf_rn(w2f, __fmul_rn(du, du), fu);
+      if (!(cand < best)) break;
+      best = cand; v = u; fv = fu; dv = du;
+    }
+    w.v = v; w.fv = fv; w.dv = dv;
+    w.v1 = next_vertex<TX>(ln, v, b);
+    if (w.v1 >= 0) { w.fv1 = ln.fval(w.v1); w.dv1 = (float)(lo - w.v1); }
+  }
+}
+
+template <int Bytes, int TX, bool Epilogue, bool UseTMA, bool Wide>
 __global__ void __launch_bounds__(Wide ? 1024 : 512, Wide ? 1 : 3)
 later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
                        const typename LabelOf<Bytes>::type* __restrict__ labels,
                        float* __restrict__ f, LineGeom g, TileBoxes tb, float w2,
-                       int border_lo, int border_hi, int flags, int code_bit) {
+                       int border_lo, int border_hi, int flags) {
   using LT = typename LabelOf<Bytes>::type;
   extern __shared__ __align__(128) unsigned char smem_tile[];
   constexpr int SUBS = 32 / TX;                       // chunks handled side by side by one warp
@@ -815,7 +762,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
     uint32_t wstart = 0, wzero = 0;
     if (live) {
       uint32_t idx = (uint32_t)i0 * ls + (uint32_t)x;
-      LT prev = (!FromCodes && i0 > 0) ? tl[idx - ls] : (LT)0;
+      LT prev = (i0 > 0) ? tl[idx - ls] : (LT)0;
       uint32_t fdst = fs_a + (uint32_t)i0 * ROW + (uint32_t)x * 4u;
       if (i0 + 32 <= n) {
 #pragma unroll
@@ -823,28 +770,18 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           const LT here = tl[idx];
           if (!UseTMA) sts_f32(fdst + r * ROW, tf[idx]);
           idx += ls;
-          if (FromCodes) {
-            if (here & code_bit) wstart |= (1u << r);
-            if (Epilogue && (here & 4)) wzero |= (1u << r);
-          } else {
-            if (here != prev) wstart |= (1u << r);
-            if (Epilogue && here == 0) wzero |= (1u << r);
-            prev = here;
-          }
+          if (here != prev) wstart |= (1u << r);
+          if (Epilogue && here == 0) wzero |= (1u << r);
+          prev = here;
         }
       } else {
         for (int r = 0; r < n - i0; ++r) {
           const LT here = tl[idx];
           if (!UseTMA) sts_f32(fdst + r * ROW, tf[idx]);
           idx += ls;
-          if (FromCodes) {
-            if (here & code_bit) wstart |= (1u << r);
-            if (Epilogue && (here & 4)) wzero |= (1u << r);
-          } else {
-            if (here != prev) wstart |= (1u << r);
-            if (Epilogue && here == 0) wzero |= (1u << r);
-            prev = here;
-          }
+          if (here != prev) wstart |= (1u << r);
+          if (Epilogue && here == 0) wzero |= (1u << r);
+          prev = here;
         }
         wstart |= 1u << (n - i0);          // pretend a run starts at row n (line end)
       }
@@ -871,8 +808,16 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   const uint32_t cflagcol = cflag_a + (uint32_t)x;
   char* const line0 = reinterpret_cast<char*>(tf + x);
 
-  // ============ stage 1: runs of length one; hulls of every other run, chunk by chunk ============
-  int crossing = 0;                                        // does any of my chunks hold an open segment?
+  // ============ stage 1: everything that can be finished inside a chunk ============
+  // Per chunk (32 rows of one line): the rows are cut into segments by the run starts; a segment
+  // is LOCAL when its run lies inside the chunk and CROSSING when the run goes on in the chunk
+  // below and / or above.
+  //   (1a) runs of length one: min(f, w2), straight-line predicated code;
+  //   (1b) which segments are constant (no scan needed), from one pass over the samples;
+  //   (1c) hulls of all non-constant segments, ONE loop over their rows (build_hull_rows);
+  //   (1d) outputs of the local runs, ONE loop over their rows (read_out_rows_local).
+  // The hull bits of the crossing segments go to hullw for stages 2 and 3.
+  int any_cross = 0;
   if (live) {
     for (int c = chunk0; c < nchunks; c += chunk_step) {
       const int i0 = c << 5;
@@ -884,126 +829,84 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       uint32_t ext = 1u;
       if (i0 + 32 < n) ext = lds_u32(startcol + (uint32_t)(c + 1) * ROW) & 1u;
       const uint32_t nextw = (wstart >> 1) | (ext << 31);
-      uint32_t single = wstart & nextw;                    // runs of length one
+      uint32_t single = wstart & nextw & rowmask;          // runs of length one
       if (!border_lo && c == 0) single &= ~1u;             // rows lacking a border term go the long way
       if (!border_hi && i0 + 32 >= n) single &= ~(1u << (n - 1 - i0));
 
-      // (1a) runs of length one: min(f, w2); value computed unconditionally, store predicated
-      const uint32_t fp0 = ln.f + (uint32_t)i0 * ROW;
-      char* const op0 = line0 + (size_t)i0 * pitch;
-      if (rows == 32) {
-        char* op = op0;
+      // (1a) runs of length one: value computed unconditionally, store predicated
+      if (single) {
+        const uint32_t fp0 = ln.f + (uint32_t)i0 * ROW;
+        char* const op0 = line0 + (size_t)i0 * pitch;
+        if (rows == 32) {
+          char* op = op0;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          float v = fminf(lds_f32(fp0 + r * ROW), w2);
-          if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
-          if (single & (1u << r)) *reinterpret_cast<float*>(op) = v;
-          op += pitch;
-        }
-      } else {
-        for (int r = 0; r < rows; ++r) {
-          float v = fminf(lds_f32(fp0 + r * ROW), w2);
-          if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
-          if (single & (1u << r)) *reinterpret_cast<float*>(op0 + (size_t)r * pitch) = v;
+          for (int r = 0; r < 32; ++r) {
+            float v = fminf(lds_f32(fp0 + r * ROW), w2);
+            if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
+            if (single & (1u << r)) *reinterpret_cast<float*>(op) = v;
+            op += pitch;
+          }
+        } else {
+          for (int r = 0; r < rows; ++r) {
+            float v = fminf(lds_f32(fp0 + r * ROW), w2);
+            if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
+            if (single & (1u << r)) *reinterpret_cast<float*>(op0 + (size_t)r * pitch) = v;
+          }
         }
       }
 
-      // (1b) every other run that starts in this chunk.  Runs of at most 32 rows -- even when they
-      // spill into the next chunk -- are finished here with their hull in a register (bits relative
-      // to the run start).  Longer runs only get the hull of their rows in this chunk, recorded in
-      // hullw (bits relative to i0), and are stitched and read out in stages 2 and 3.
       uint32_t hb = 0u;
-      uint32_t cflags = 0u;
-      bool has_long = false;
-      const uint32_t todo = wstart & rowmask & ~single;
-      int next_start = -1;                                 // first run start after this chunk (lazy)
-      for (uint32_t rest = todo; rest;) {
-        const int r0 = __ffs(rest) - 1;
-        rest &= rest - 1u;
-        const uint32_t mhi = nextw & (0xffffffffu << r0);
-        const int sa = i0 + r0;
-        int sb;
-        if (mhi) {
-          sb = i0 + __ffs(mhi);
-        } else {                                           // the run leaves this chunk: where does it end?
-          if (next_start < 0) {
-            next_start = n;
-            for (int cc = c + 1; cc < nchunks; ++cc) {
-              const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
-              if (w) { next_start = min(n, (cc << 5) + __ffs(w) - 1); break; }
-            }
-          }
-          sb = next_start;
-        }
-        float f0;
-        if (sb - sa <= 32) {
-          const bool lo_b = sa > 0 || border_lo, hi_b = sb < n || border_hi;
-          if (segment_constant<TX>(ln, sa, sb, f0)) {
-            char* dst = line0 + (size_t)sa * pitch;
-            uint32_t sq_lo = sq_t + 4u, sq_hi = sq_t + (uint32_t)(sb - sa) * 4u;
-            for (int i = sa; i < sb; ++i) {
-              float best = f0;
-              if (lo_b) best = fminf(best, lds_f32(sq_lo));
-              if (hi_b) best = fminf(best, lds_f32(sq_hi));
-              sq_lo += 4u; sq_hi -= 4u;
-              if (Epilogue) best = finish_value(best, (wzero >> r0) & 1u, flags);
-              *reinterpret_cast<float*>(dst) = best;
-              dst += pitch;
-            }
-          } else {
-            const uint32_t lb = build_hull<TX>(ln, sa, sa, sb, w2d, 0u);
-            read_out_local<TX, Epilogue>(ln, lb, sa, sa, sb, w2, lo_b, hi_b, sq_t, line0, pitch,
-                                         (wzero >> r0) & 1u, flags);
-          }
-        } else {
-          if (segment_constant<TX>(ln, sa, i0 + 32, f0)) {
-            if (f0 < inf) hb |= 0xffffffffu << r0;            // every row is a vertex
-            cflags |= 2u;
-          } else {
-            hb = build_hull<TX>(ln, i0, sa, i0 + 32, w2d, hb);
-          }
-          crossing = 1;
-          has_long = true;
-        }
-      }
-      // rows of a long run that entered from the chunk below (short ones were finished by their owner)
-      if (!(wstart & 1u)) {
-        int a_lo = 0;
-        for (int cc = c - 1; cc >= 0; --cc) {
-          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
-          if (w) { a_lo = (cc << 5) + 31 - __clz(w); break; }
-        }
+      const uint32_t multi = rowmask & ~single;
+      if (multi) {
         const uint32_t wreal = wstart & rowmask;
-        int b_run;
-        if (wreal) b_run = i0 + __ffs(wreal) - 1;
-        else if (!ext) {
-          if (next_start < 0) {
-            next_start = n;
-            for (int cc = c + 1; cc < nchunks; ++cc) {
-              const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
-              if (w) { next_start = min(n, (cc << 5) + __ffs(w) - 1); break; }
+        const uint32_t starts = wreal | 1u;                // the segment entering from below starts at row 0
+        const bool entering = !(wstart & 1u), leaving = !ext;
+        const uint32_t ent_mask = entering ? (wreal ? ((1u << (__ffs(wreal) - 1)) - 1u) : rowmask) : 0u;
+        const int s2 = 31 - __clz(starts);                 // first row of the last segment
+        const uint32_t lea_mask = (leaving && wreal) ? (0xffffffffu << s2) : 0u;
+        const uint32_t cross_mask = ent_mask | lea_mask;
+
+        // (1b) rows whose sample differs from the row below, then the rows of non-constant segments
+        uint32_t breaks = 0u;
+        {
+          uint32_t at = ln.f + (uint32_t)i0 * ROW;
+          float prev = lds_f32(at);
+          if (rows == 32) {
+#pragma unroll
+            for (int r = 1; r < 32; ++r) {
+              const float cur = lds_f32(at + r * ROW);
+              if (cur != prev) breaks |= 1u << r;
+              prev = cur;
+            }
+          } else {
+            for (int r = 1; r < rows; ++r) {
+              const float cur = lds_f32(at + r * ROW);
+              if (cur != prev) breaks |= 1u << r;
+              prev = cur;
             }
           }
-          b_run = next_start;
-        } else b_run = min(n, i0 + 32);
-        if (b_run - a_lo > 32) {
-          const int seg_end = min(b_run, i0 + rows);
-          float f0;
-          if (segment_constant<TX>(ln, i0, seg_end, f0)) {
-            if (f0 < inf) hb |= (seg_end - i0 == 32) ? 0xffffffffu : ((1u << (seg_end - i0)) - 1u);
-            cflags |= 1u;
-          } else {
-            hb = build_hull<TX>(ln, i0, i0, seg_end, w2d, hb);
-          }
-          crossing = 1;
-          has_long = true;
         }
+        const uint32_t noncst = nonconstant_rows(starts, breaks & ~starts & rowmask) & multi;
+        // a constant crossing segment is its own hull: equal heights never hide one another
+        if (cross_mask) {
+          uint32_t cflags = 0u;
+          if (ent_mask && !(noncst & ent_mask)) { cflags |= 1u; if (ln.fval(i0) < inf) hb |= ent_mask; }
+          if (lea_mask && !(noncst & lea_mask)) { cflags |= 2u; if (ln.fval(i0 + s2) < inf) hb |= lea_mask; }
+          sts_u8(cflagcol + (uint32_t)c * TX, cflags);
+          any_cross = 1;
+        }
+        // (1c) hulls of the non-constant segments
+        if (noncst) hb = build_hull_rows<TX>(ln, i0, noncst, starts, w2d, hb);
+        // (1d) the local runs are finished here
+        const uint32_t local = multi & ~cross_mask;
+        if (local)
+          read_out_rows_local<TX, Epilogue>(ln, i0, local, starts, nextw, noncst, hb, wzero, n, w2, border_lo,
+                                            border_hi, sq_t, line0, pitch, flags);
       }
       sts_u32(ln.hull + (uint32_t)c * ROW, hb);
-      if (has_long) sts_u8(cflagcol + (uint32_t)c * TX, cflags);   // only ever read for chunks on long runs
     }
   }
-  if (!__syncthreads_or(crossing)) return;                 // every run was finished inside its chunk
+  if (!__syncthreads_or(any_cross)) return;                // every run was finished inside its chunk
 
   // ============ stage 2: stitch the hulls of runs that cross chunk boundaries ============
   // Divide and conquer over the chunks: at level l the groups of 2^(l-1) chunks left and right
@@ -1073,56 +976,69 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
     __syncthreads();
   }
 
-  // ============ stage 3: outputs of the run segments that cross chunk boundaries ============
+  // ============ stage 3: outputs of the crossing segments, ONE loop over their rows per chunk ============
   if (live) {
     for (int c = chunk0; c < nchunks; c += chunk_step) {
       const int i0 = c << 5;
       const int rows = min(32, n - i0);
+      const uint32_t rowmask = rows == 32 ? 0xffffffffu : ((1u << rows) - 1u);
       const uint32_t wstart = lds_u32(startcol + (uint32_t)c * ROW);
       const uint32_t wzero = Epilogue ? lds_u32(zerocol + (uint32_t)c * ROW) : 0u;
-      const bool open_lo = !(wstart & 1u);                              // only possible for c > 0
-      bool open_hi = false;
-      if (i0 + 32 < n) open_hi = !(lds_u32(startcol + (uint32_t)(c + 1) * ROW) & 1u);
-      if (!open_lo && !open_hi) continue;
-      const uint32_t wreal = wstart & (rows == 32 ? 0xffffffffu : ((1u << rows) - 1u));
+      const bool entering = !(wstart & 1u);                             // only possible for c > 0
+      bool leaving = false;
+      if (i0 + 32 < n) leaving = !(lds_u32(startcol + (uint32_t)(c + 1) * ROW) & 1u);
+      if (!entering && !leaving) continue;
+      const uint32_t wreal = wstart & rowmask;
+      const int s2 = 31 - __clz(wreal | 1u);                            // first row of the last segment
+      const uint32_t ent_mask = entering ? (wreal ? ((1u << (__ffs(wreal) - 1)) - 1u) : rowmask) : 0u;
+      const uint32_t lea_mask = (leaving && wreal) ? (0xffffffffu << s2) : 0u;
 
-      int a_lo = 0, b_hi = min(n, i0 + 32);
-      if (open_lo) {                                                    // run start below this chunk
-        for (int cc = c - 1; cc >= 0; --cc) {
-          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
-          if (w) { a_lo = (cc << 5) + 31 - __clz(w); break; }
+      HullWalk w;
+      w.a = w.b = 0; w.v = w.v1 = -1; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
+      w.lo_b = w.hi_b = false; w.cst = true; w.bg = false;
+      for (uint32_t rest = ent_mask | lea_mask; rest; rest &= rest - 1u) {
+        const int r = __ffs(rest) - 1;
+        const int i = i0 + r;
+        if (r == 0 || (lea_mask && r == s2)) {                          // first row of a segment: set the walk up
+          int a = i, b;
+          if (r == 0 && entering) {                                     // the run started below this chunk
+            a = 0;
+            for (int cc = c - 1; cc >= 0; --cc) {
+              const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
+              if (ws) { a = (cc << 5) + 31 - __clz(ws); break; }
+            }
+          }
+          if (r == 0 && entering && wreal) {
+            b = i0 + __ffs(wreal) - 1;                                  // ... and ends inside it
+          } else if (leaving) {                                         // the run ends above this chunk
+            b = n;
+            for (int cc = c + 1; cc < nchunks; ++cc) {
+              const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
+              if (ws) { b = min(n, (cc << 5) + __ffs(ws) - 1); break; }
+            }
+          } else {
+            b = min(n, i0 + 32);
+          }
+          walk_begin<TX>(w, ln, cflagcol, i, a, b, n, w2, border_lo != 0, border_hi != 0, (wzero >> r) & 1u);
         }
-      }
-      if (open_hi) {                                                    // run end above this chunk
-        b_hi = n;
-        for (int cc = c + 1; cc < nchunks; ++cc) {
-          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
-          if (w) { b_hi = min(n, (cc << 5) + __ffs(w) - 1); break; }
+        float best = inf;
+        if (w.cst) {
+          best = ln.fval(i);
+        } else if (w.v >= 0) {
+          best = __fmaf_rn(w2, __fmul_rn(w.dv, w.dv), w.fv);
+          while (w.v1 >= 0) {
+            const float cand = __fmaf_rn(w2, __fmul_rn(w.dv1, w.dv1), w.fv1);
+            if (!(cand <= best)) break;
+            best = cand; w.v = w.v1; w.fv = w.fv1; w.dv = w.dv1;
+            w.v1 = next_vertex<TX>(ln, w.v1, w.b);
+            if (w.v1 >= 0) { w.fv1 = ln.fval(w.v1); w.dv1 = (float)(i - w.v1); }
+          }
+          w.dv += 1.0f; w.dv1 += 1.0f;
         }
-      }
-      if (open_lo) {
-        const int hi = wreal ? (i0 + __ffs(wreal) - 1) : (i0 + rows);   // rows of this chunk in the run
-        const int b = wreal ? hi : b_hi;
-        if (b - a_lo > 32) {                                            // short runs were finished in stage 1
-          if (run_is_constant<TX>(ln, cflagcol, a_lo, b))
-            write_constant_run<TX, Epilogue>(ln, i0, hi, a_lo, b, a_lo > 0 || border_lo, b < n || border_hi, sq_t,
-                                             line0, pitch, wzero & 1u, flags);
-          else
-            read_out<TX, Epilogue>(ln, i0, hi, a_lo, b, w2, a_lo > 0 || border_lo, b < n || border_hi, sq_t,
-                                   line0, pitch, wzero & 1u, flags);
-        }
-      }
-      if (open_hi && wreal) {                                           // a run starting here and leaving above
-        const int r0 = 31 - __clz(wreal);
-        const int lo = i0 + r0;
-        if (b_hi - lo > 32) {
-          if (run_is_constant<TX>(ln, cflagcol, lo, b_hi))
-            write_constant_run<TX, Epilogue>(ln, lo, i0 + 32, lo, b_hi, lo > 0 || border_lo, b_hi < n || border_hi,
-                                             sq_t, line0, pitch, (wzero >> r0) & 1u, flags);
-          else
-            read_out<TX, Epilogue>(ln, lo, i0 + 32, lo, b_hi, w2, lo > 0 || border_lo, b_hi < n || border_hi, sq_t,
-                                   line0, pitch, (wzero >> r0) & 1u, flags);
-        }
+        if (w.lo_b) best = fminf(best, lds_f32(sq_t + (uint32_t)(i - w.a + 1) * 4u));
+        if (w.hi_b) best = fminf(best, lds_f32(sq_t + (uint32_t)(w.b - i) * 4u));
+        if (Epilogue) best = finish_value(best, w.bg, flags);           // a run has one label
+        *reinterpret_cast<float*>(line0 + (size_t)i * pitch) = best;
       }
     }
   }

@@ -19,43 +19,11 @@ sys.path.insert(0, ROOT)
 import edt_b200  # noqa: E402
 
 
+from edt_b200 import workloads  # noqa: E402
+
+
 def gen(name, n, dev):
-  g = torch.Generator(device=dev)
-  g.manual_seed(0)
-  if name == "cfg2":        # iid labels 0..255
-    return torch.randint(0, 256, (n, n, n), dtype=torch.int32, device=dev, generator=g), (1, 1, 1), False
-  if name == "cfg2b":       # 32^3 constant blocks of random labels
-    small = torch.randint(0, 256, (n // 32,) * 3, dtype=torch.int32, device=dev, generator=g)
-    big = small.repeat_interleave(32, 0).repeat_interleave(32, 1).repeat_interleave(32, 2)
-    return big.contiguous(), (1, 1, 1), False
-  if name == "blocks8":     # 8^3 blocks
-    small = torch.randint(0, 256, (n // 8,) * 3, dtype=torch.int32, device=dev, generator=g)
-    big = small.repeat_interleave(8, 0).repeat_interleave(8, 1).repeat_interleave(8, 2)
-    return big.contiguous(), (1, 1, 1), False
-  if name == "cfg3":        # all ones uint8, anisotropic, black border
-    return torch.ones((n, n, n), dtype=torch.uint8, device=dev), (6, 6, 30), True
-  if name == "ones_nobb":   # all ones, no border: everything stays +inf
-    return torch.ones((n, n, n), dtype=torch.uint8, device=dev), (1, 1, 1), False
-  if name in ("balls", "voronoi"):
-    ax = torch.arange(n, device=dev, dtype=torch.float32)
-    z, y, x = ax.view(n, 1, 1), ax.view(1, n, 1), ax.view(1, 1, n)
-    if name == "balls":     # 64 random balls, binary
-      lab = torch.zeros((n, n, n), dtype=torch.uint8, device=dev)
-      c = torch.rand((64, 3), device=dev, generator=g) * n
-      r = (40 + 50 * torch.rand((64,), device=dev, generator=g)) * (n / 512.0)
-      for k in range(64):
-        lab |= (((z - c[k, 0]) ** 2 + (y - c[k, 1]) ** 2 + (x - c[k, 2]) ** 2) <= r[k] ** 2).to(torch.uint8)
-      return lab, (1, 1, 1), False
-    c = torch.rand((200, 3), device=dev, generator=g) * n      # voronoi cells of 200 seeds
-    best = torch.full((n, n, n), float("inf"), device=dev)
-    lab = torch.zeros((n, n, n), dtype=torch.int32, device=dev)
-    for k in range(200):
-      d = (z - c[k, 0]) ** 2 + (y - c[k, 1]) ** 2 + (x - c[k, 2]) ** 2
-      m = d < best
-      best = torch.where(m, d, best)
-      lab = torch.where(m, torch.full_like(lab, k + 1), lab)
-    return lab, (1, 1, 1), False
-  raise ValueError(name)
+  return workloads.generate(name, n, dev)
 
 
 def main():
