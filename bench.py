@@ -119,6 +119,30 @@ class ClockSampler:
             "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_description():
+  """CPU model / sockets / cores of this box, the affinity of this process and the load average:
+  what the CPU arm's number depends on (SURVEY.md section 8d asks for them beside it)."""
+  info = {"cpu_count": os.cpu_count()}
+  try:
+    info["affinity"] = len(os.sched_getaffinity(0))
+  except Exception:
+    pass
+  try:
+    out = subprocess.run(["lscpu"], capture_output=True, text=True, timeout=10).stdout
+    for line in out.splitlines():
+      key, _, val = line.partition(":")
+      key = key.strip()
+      if key in ("Model name", "Socket(s)", "Core(s) per socket", "Thread(s) per core", "NUMA node(s)"):
+        info[key.lower().replace("(s)", "s").replace(" ", "_")] = val.strip()
+  except Exception:
+    pass
+  try:
+    info["loadavg_1m"] = os.getloadavg()[0]
+  except Exception:
+    pass
+  return info
+
+
 def dist_env():
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -151,9 +175,12 @@ def reference_arm(args):
   sample = np.asfortranarray(labels[:, :, :depth])
   for _ in range(args.warmup):
     ref.edtsq(sample, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
+  step_s = []
   t0 = time.perf_counter()
   for _ in range(args.steps):
+    t1 = time.perf_counter()
     ref.edtsq(sample, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
+    step_s.append(time.perf_counter() - t1)
   dt = time.perf_counter() - t0
   mvox = sample.size * args.steps / dt / 1e6
   sample_desc = "512x512x%d Z slab of the workload per step, parallel=%d threads" % (depth, cores)
@@ -163,7 +190,12 @@ def reference_arm(args):
     "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": None, "dtype": "f32 (f64 envelope internals)", "data": "synthetic",
     "config": {"workload": WORKLOAD, "sample": sample_desc},
-    "cpu_baseline": {"value": mvox, "unit": "Mvoxels/s", "cores": cores, "kind": kind, "sample": sample_desc},
+    "cpu_baseline": {"value": mvox, "unit": "Mvoxels/s", "cores": cores, "kind": kind, "sample": sample_desc,
+                     "best_step_value": sample.size / min(step_s) / 1e6,
+                     "threads": "the reference's own thread pool, parallel=%d, not pinned (the reference has no "
+                                "affinity control); the box's load and NUMA placement move this number between "
+                                "boxes, see `host`" % cores,
+                     "host": host_description()},
     "e2e": {"value": mvox, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "gpu_launches": 0,
   }
@@ -188,12 +220,18 @@ def cpu_baseline_leg():
   ref.edtsq(probe, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
   rate = probe.size / (time.perf_counter() - t0)
   depth = int(min(SHAPE[2], max(32, (rate * 15.0) // (SHAPE[0] * SHAPE[1]) // 32 * 32)))
+  depth = max(32, depth // 3 // 32 * 32)              # three repetitions share the ~15 s budget
   sample = np.asfortranarray(labels[:, :, :depth])
-  t0 = time.perf_counter()
-  ref.edtsq(sample, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
-  dt = time.perf_counter() - t0
+  times = []
+  for _ in range(3):
+    t0 = time.perf_counter()
+    ref.edtsq(sample, anisotropy=ANISOTROPY, black_border=False, parallel=cores)
+    times.append(time.perf_counter() - t0)
+  dt = min(times)
   out = {"value": sample.size / dt / 1e6, "unit": "Mvoxels/s", "cores": cores, "kind": kind,
-         "sample": "one edtsq of a 512x512x%d Z slab of the workload (%.1f s), parallel=%d" % (depth, dt, cores)}
+         "sample": "best of 3 edtsq calls on a 512x512x%d Z slab of the workload (%.1f s each), parallel=%d, "
+                   "threads not pinned" % (depth, dt, cores),
+         "all_runs_s": times, "host": host_description()}
   if cores > 1:
     # the same code on ONE thread (SURVEY.md section 8d asks for both), on a thinner slab
     thin = np.asfortranarray(labels[:, :, :max(32, depth // 8)])
@@ -203,6 +241,79 @@ def cpu_baseline_leg():
     out["single_thread"] = {"value": thin.size / dt1 / 1e6, "unit": "Mvoxels/s",
                             "sample": "512x512x%d slab (%.1f s), parallel=1" % (thin.shape[2], dt1)}
   return out
+
+
+def workload_matrix(dev, peak, steps=5):
+  """Device-resident transform times of the structured workloads of SURVEY.md section 8d (the
+  headline workload has run length ~1 and never runs the envelope scan; these do)."""
+  import torch
+  import edt_b200
+  from edt_b200 import workloads
+  rows = []
+  n = SHAPE[0]
+  for name, sqrt in (("cfg2", False), ("cfg2b", False), ("cfg3", False), ("cfg3", True), ("balls", False),
+                     ("voronoi", False)):
+    lab, an, bb = workloads.generate(name, n, dev)
+    out = torch.empty(lab.shape, dtype=torch.float32, device=dev)
+    for _ in range(3):
+      edt_b200.edt_cuda(lab, an, bb, sqrt=sqrt, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      edt_b200.edt_cuda(lab, an, bb, sqrt=sqrt, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    L = lab.element_size()
+    alg = (3 * L + 20) * lab.numel()
+    rows.append({"workload": name, "function": "edt" if sqrt else "edtsq", "shape": [n, n, n], "label_bytes": L,
+                 "anisotropy": list(an), "black_border": bb, "ms": ms, "Mvoxels_s": lab.numel() / ms / 1e3,
+                 "algorithmic_GBps": alg / ms / 1e6, "frac": alg / ms / 1e6 / peak})
+    del lab, out
+    torch.cuda.empty_cache()
+  return rows
+
+
+def pageable_e2e(labels_np, steps=3):
+  """edt_b200.edtsq(ndarray): the drop-in call with a plain (pageable) numpy array in and out."""
+  import edt_b200
+  edt_b200.edtsq(labels_np, anisotropy=ANISOTROPY, black_border=False)
+  times = []
+  for _ in range(steps):
+    t0 = time.perf_counter()
+    res = edt_b200.edtsq(labels_np, anisotropy=ANISOTROPY, black_border=False)
+    times.append(time.perf_counter() - t0)
+  best = min(times)
+  return {"value": labels_np.size / best / 1e6, "unit": "Mvoxels/s", "ms_per_call": best * 1e3,
+          "all_calls_ms": [t * 1e3 for t in times],
+          "note": "edt_b200.edtsq(numpy array), pageable memory both ways (staged through pinned buffers by "
+                  "the library's copy threads), best of %d" % steps}, res
+
+
+def slab_parity_check(dev, rank, world, passes, peer_halo_factory):
+  """Before anything is timed at N > 1: a structured 512 x 512 x (64*world) volume (32^3 blocks of
+  labels with background) is transformed by the slab-split path (edtsq and sdf) and every rank
+  compares ITS slab with the same rows of the single-GPU transform of the whole volume."""
+  import torch
+  import torch.distributed as dist
+  import edt_b200
+  import edt_b200.distributed as ed
+  from edt_b200 import workloads
+  depth = 64
+  lab, _, _ = workloads.generate("cfg2b", SHAPE[0], dev, nz=depth * world)      # same seed on every rank
+  lab = (lab % 7).to(torch.int32)                                               # label 0 = background
+  mine = lab[rank * depth:(rank + 1) * depth].contiguous()
+  an_zyx = (2.0, 1.0, 1.0)
+  ok = True
+  for signed, sqrt in ((False, False), (True, True)):
+    whole = edt_b200.edt_cuda(lab, an_zyx, False, sqrt=sqrt, signed=signed)
+    got = ed.slab_transform(mine, an_zyx, False, sqrt=sqrt, signed=signed, passes=passes,
+                            depths=[depth] * world, peer_halo=peer_halo_factory(depth))
+    ok = ok and bool(torch.equal(got, whole[rank * depth:(rank + 1) * depth]))
+  flag = torch.tensor([1 if ok else 0], device=dev)
+  dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+  return bool(flag.item())
 
 
 def ours(args):
@@ -259,6 +370,13 @@ def ours(args):
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)            # all ranks or none
     if int(ok.item()) == 0:
       peer_halo = None
+    def halo_for(depth):
+      # the parity volume has thinner slabs than the timed one: its own staging buffer
+      ph, _ = ed.make_peer_halo(dev, sy, sx, torch.int32, 8)
+      okp = torch.tensor([1 if ph is not None else 0], device=dev)
+      dist.all_reduce(okp, op=dist.ReduceOp.MIN)
+      return ph if int(okp.item()) == 1 else None
+    parity_checked = slab_parity_check(dev, rank, world, passes, halo_for)
     verdicts = []
     def step(events=None):
       # the halo path's exactness verdict is a device flag; it is read for all steps at once,
@@ -325,7 +443,9 @@ def ours(args):
   if world > 1:
     # the exchange dominates: report the whole step against HBM for orientation only
     alg = (3 * LABEL_BYTES + 20) * nvox
-    roofline = {"bound": "hbm", "kernel": "whole slab step (3 passes + Z-slab<->Y-slab exchange)",
+    roofline = {"bound": "hbm", "kernel": "whole slab step (X, Y, Z passes + %s)" % (
+                    "face fix-up reading the neighbours' faces" if result.get("method") == "halo"
+                    else "Z-slab<->Y-slab transposes"),
                 "achieved": alg / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg / (ms_per_step * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
                 "nvlink_bytes_per_gpu_per_step": (2 * 512 * 512 * (32 * 4 + LABEL_BYTES + 1)
@@ -367,6 +487,10 @@ def ours(args):
                    "timing": "CUDA events on the launch stream, max over ranks"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": (7 if result.get("method") == "halo" else 3) * args.steps,
         "clocks": clocks,
+        "parity_checked": parity_checked,
+        "parity_check": "before timing: edtsq and sdf of a 512x512x%d volume of 32^3 label blocks (with background, "
+                        "anisotropy 2 along z) through the slab split, every rank's slab bit-equal to the same rows "
+                        "of the single-GPU transform" % (64 * world),
       }
       print(json.dumps(line), flush=True)
     dist.destroy_process_group()
@@ -456,6 +580,17 @@ def ours(args):
       "clocks": clocks,
       "device_equals_host_path": same,
     }
+    if world == 1:
+      try:
+        line["workloads"] = workload_matrix(dev, peak)
+      except Exception as exc:
+        line["workloads"] = {"error": repr(exc)}
+      try:
+        line["e2e"]["pageable"], res_np = pageable_e2e(labels_np)
+        line["e2e"]["pageable"]["equals_device_path"] = bool(np.array_equal(res_np, f_dev.cpu().numpy().T))
+        del res_np
+      except Exception as exc:
+        line["e2e"]["pageable"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
       try:
         line["cpu_baseline"] = cpu_baseline_leg()

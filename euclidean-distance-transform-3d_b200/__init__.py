@@ -32,7 +32,7 @@ __version__ = "0.1.0"
 __all__ = [
   "edt", "edtsq", "sdf", "sdfsq",
   "edt1d", "edt1dsq", "edt2d", "edt2dsq", "edt3d", "edt3dsq",
-  "edt_cuda", "transform_batch", "each", "each_cuda", "device_count", "library_path", "EDTError",
+  "edt_cuda", "transform_batch", "each", "each_cuda", "label_stats_cuda", "device_count", "library_path", "EDTError",
 ]
 
 FLAG_SQRT = 1
@@ -50,7 +50,10 @@ class EDTError(RuntimeError):
 
 
 def library_path():
-  return os.path.join(_HERE, "libedt_b200.so")
+  """The CUDA library built in-tree by __graft_entry__.build().  EDTB200_LIBRARY overrides the
+  path (A/B measurements of two builds on the same box); it is still this library, never a
+  CPU substitute."""
+  return os.environ.get("EDTB200_LIBRARY") or os.path.join(_HERE, "libedt_b200.so")
 
 
 def _lib():
@@ -86,6 +89,10 @@ def _lib():
   lib.edtb200_profile_passes.restype = ci
   lib.edtb200_pass_ms.argtypes = [ci, vp]
   lib.edtb200_pass_ms.restype = ci
+  lib.edtb200_label_stats.argtypes = [vp, ci, vp, i64, i64, i64, ci, vp, vp, vp, vp, vp, vp, ci, vp]
+  lib.edtb200_label_stats.restype = ci
+  lib.edtb200_label_extract.argtypes = [vp, ci, vp, i64, i64, i64, ctypes.c_uint64, vp, ci, vp, ci, vp]
+  lib.edtb200_label_extract.restype = ci
   lib.edtb200_release.restype = ci
   _LIB = lib
   return lib
@@ -485,17 +492,158 @@ def transform_batch(volumes, anisotropy=None, black_border=False, *, sqrt=False,
 # masked image per label (src/edt.pyx:951-994; README.md:23, 204)
 # ---------------------------------------------------------------------------------------
 
-def each(labels, dt, in_place=False):
+def label_stats_cuda(labels, dt):
+  """Per-label statistics of a finished transform in ONE pass on the device: a dict of torch CUDA
+  tensors sorted by label -- "labels" (int64, background 0 skipped), "count" (voxels), "max"
+  (largest distance), "argmax" (smallest C-order linear index where it is attained), "box"
+  (n x 6: inclusive bounding box, low corner then high corner, in ARRAY axis order).
+  `labels` and `dt` are C-contiguous CUDA tensors of the same 1-3 dim shape (kernels:
+  csrc/edt_each.cuh; the reference builds the same information from run lists,
+  src/edt_voxel_graph.hpp:238-275)."""
+  import torch
+  if not (isinstance(labels, torch.Tensor) and labels.is_cuda and isinstance(dt, torch.Tensor) and dt.is_cuda):
+    raise TypeError("label_stats_cuda expects torch CUDA tensors")
+  if labels.shape != dt.shape or labels.device != dt.device:
+    raise ValueError("labels and dt must have the same shape and device")
+  nbytes = _torch_label_bytes(torch).get(labels.dtype)
+  if nbytes is None:
+    raise TypeError("label_stats_cuda: unsupported label dtype %s" % labels.dtype)
+  labels = labels.contiguous()
+  dt = dt.contiguous().to(torch.float32)
+  nd = labels.dim()
+  dims = [int(d) for d in labels.shape][::-1] + [1] * (3 - nd)          # sx, sy, sz
+  dev = labels.device
+  stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+  capacity = 1024
+  while True:
+    keys = torch.empty(capacity, dtype=torch.int64, device=dev)
+    count = torch.empty(capacity, dtype=torch.int64, device=dev)
+    mx = torch.empty(capacity, dtype=torch.float32, device=dev)
+    argmax = torch.empty(capacity, dtype=torch.int64, device=dev)
+    box = torch.empty((capacity, 6), dtype=torch.int32, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    _check(_lib().edtb200_label_stats(labels.data_ptr(), nbytes, dt.data_ptr(), dims[0], dims[1], dims[2],
+                                      capacity, keys.data_ptr(), count.data_ptr(), mx.data_ptr(),
+                                      argmax.data_ptr(), box.data_ptr(), overflow.data_ptr(), dev.index, stream))
+    used = int((keys != 0).sum().item())
+    if int(overflow.item()) == 0 and 2 * used <= capacity:
+      break
+    capacity *= 4                                    # table too full (or full): again with more room
+  sel = torch.nonzero(keys != 0).flatten()
+  order = sel[torch.argsort(_unsigned_sort_key(torch, keys[sel], nbytes))]
+  b = box[order].to(torch.int64)
+  lo = b[:, :nd].flip(1)                             # x0 y0 z0 -> array axis order
+  hi = b[:, 3:3 + nd].flip(1)
+  return {"labels": keys[order], "count": count[order], "max": mx[order], "argmax": argmax[order],
+          "box": torch.cat([lo, hi], dim=1)}
+
+
+def _unsigned_sort_key(torch, keys, nbytes):
+  """Sort key that orders int64-held label bits as the unsigned integers they are."""
+  if nbytes < 8:
+    return keys
+  return keys ^ torch.tensor(-0x8000000000000000, dtype=torch.int64, device=keys.device)
+
+
+def _label_scalar(torch, key, dtype):
+  """The label value a table key (the label's raw bits, zero-extended) stands for."""
+  nbytes = torch.empty((), dtype=dtype).element_size()
+  raw = np.array([key & ((1 << (8 * nbytes)) - 1)], dtype=np.dtype("u%d" % nbytes))
+  if dtype == torch.bool:
+    return bool(raw[0])
+  if dtype.is_floating_point:
+    return float(raw.view(np.dtype("f%d" % nbytes))[0])
+  if dtype == torch.uint8:
+    return int(raw[0])
+  return int(raw.view(np.dtype("i%d" % nbytes))[0])      # torch's other integer types are signed
+
+
+def each_cuda(labels, dt, in_place=False, *, _stats=None):
+  """Device-resident `each` (reference: edt.each, src/edt.pyx:951-994): iterator over
+  (label, dt masked to that label) as torch CUDA tensors, labels in ascending order of their raw
+  bits (the reference's order is that of a hash map), background skipped.
+  One pass of `label_stats_cuda` finds every label's bounding box; each image is then drawn by a
+  kernel that touches only that box (the device equivalent of the reference's run-list
+  transfer).  in_place=True reuses ONE image: the previous label's box is erased, the next one
+  drawn -- do not keep references to it between iterations (the reference marks it read-only)."""
+  import torch
+  stats = _stats if _stats is not None else label_stats_cuda(labels, dt)
+  labels = labels.contiguous()
+  dt = dt.contiguous().to(torch.float32)
+  nbytes = _torch_label_bytes(torch)[labels.dtype]
+  nd = labels.dim()
+  dims = [int(d) for d in labels.shape][::-1] + [1] * (3 - nd)
+  dev = labels.device
+  keys = stats["labels"].tolist()
+  boxes = stats["box"].tolist()
+  lib = _lib()
+
+  class DeviceImageIterator:
+    def __len__(self):
+      return len(keys)
+
+    def __iter__(self):
+      img = torch.zeros(labels.shape, dtype=torch.float32, device=dev) if in_place else None
+      prev = None
+      for key, bx in zip(keys, boxes):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        lo, hi = bx[:nd][::-1] + [0] * (3 - nd), bx[nd:][::-1] + [0] * (3 - nd)      # -> x y z order
+        cbox = (ctypes.c_int * 6)(*(lo + hi))
+        out = img if in_place else torch.zeros(labels.shape, dtype=torch.float32, device=dev)
+        if in_place and prev is not None:
+          _check(lib.edtb200_label_extract(labels.data_ptr(), nbytes, dt.data_ptr(), dims[0], dims[1], dims[2],
+                                           ctypes.c_uint64(0), prev, 1, out.data_ptr(), dev.index, stream))
+        _check(lib.edtb200_label_extract(labels.data_ptr(), nbytes, dt.data_ptr(), dims[0], dims[1], dims[2],
+                                         ctypes.c_uint64(key & 0xffffffffffffffff), cbox, 0, out.data_ptr(),
+                                         dev.index, stream))
+        prev = cbox
+        yield (_label_scalar(torch, key, labels.dtype), out)
+
+  return DeviceImageIterator()
+
+
+def each(labels, dt, in_place=False, *, device=0):
   """Iterator over (label, distance transform of that label alone), labels in ascending order,
   background skipped -- same contract as the reference's edt.each (src/edt.pyx:951-994), which
-  builds it from run lists (src/edt_voxel_graph.hpp:238-310); here it is a masked copy per
-  label.  in_place=True reuses one read-only image between iterations, as the reference does."""
+  builds it from run lists (src/edt_voxel_graph.hpp:238-310).  Here labels and dt are uploaded
+  ONCE, every label's bounding box comes from one device pass (`label_stats_cuda`), each masked
+  image is drawn on the device inside that box, and only the box travels back to be pasted into
+  the host image.  in_place=True reuses one read-only image between iterations, as the reference
+  does.  Device-resident input (torch CUDA tensors) is handed to `each_cuda`."""
+  try:
+    import torch
+  except ImportError:          # pragma: no cover
+    torch = None
+  if torch is not None and isinstance(labels, torch.Tensor) and labels.is_cuda:
+    return each_cuda(labels, dt, in_place)
   labels = np.asarray(labels)
   dt = np.asarray(dt)
   if labels.shape != dt.shape:
     raise ValueError("labels and dt must have the same shape")
+  if labels.ndim < 1 or labels.ndim > 3:
+    raise TypeError("Multi-Label EDT library only supports up to 3 dimensions got {}.".format(labels.ndim))
   order = "F" if labels.flags.f_contiguous else "C"
-  keys = [k for k in np.unique(labels) if k != 0]
+  view = _label_view(labels)
+  if view is None or torch is None:
+    raise TypeError("each: unsupported label dtype %s" % labels.dtype)
+  # memory order decides the axis roles on the device; the images are pasted back in array order
+  mem = view.T if order == "F" else view
+  dmem = dt.T if order == "F" else dt
+  dev = torch.device("cuda", int(device))
+  signed = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[view.dtype.itemsize]
+  raw = np.ascontiguousarray(mem)
+  lab_t = torch.from_numpy(raw.view(np.dtype("i%d" % raw.dtype.itemsize) if raw.dtype.itemsize > 1 else np.uint8)).to(dev)
+  assert lab_t.dtype == signed
+  dt_t = torch.from_numpy(np.ascontiguousarray(dmem, dtype=np.float32)).to(dev)
+  stats = label_stats_cuda(lab_t, dt_t)
+  keys = stats["labels"].tolist()
+  boxes = stats["box"].tolist()
+  nd = labels.ndim
+  inner = each_cuda(lab_t, dt_t, in_place=True, _stats=stats)
+
+  def key_value(key):
+    # the device iterator reports the label's raw bits as an integer: back to the array's own dtype
+    return np.array([key & ((1 << (8 * view.dtype.itemsize)) - 1)], dtype=view.dtype).view(labels.dtype)[0]
 
   class ImageIterator:
     def __len__(self):
@@ -503,30 +651,25 @@ def each(labels, dt, in_place=False):
 
     def __iter__(self):
       img = np.zeros(labels.shape, dtype=np.float32, order=order) if in_place else None
-      for key in keys:
-        mask = labels == key
+      prev = None
+      for (key, dimg), bx in zip(inner, boxes):
+        sl = tuple(slice(bx[a], bx[nd + a] + 1) for a in range(nd))          # box in device-array axis order
+        sub = dimg[sl].cpu().numpy()
+        host_sl, host_sub = (sl[::-1], sub.T) if order == "F" else (sl, sub)
         if in_place:
           img.setflags(write=1)
-          img[...] = 0
-          img[mask] = dt[mask]
+          if prev is not None:
+            img[prev] = 0
+          img[host_sl] = host_sub
           img.setflags(write=0)
-          yield (key, img)
+          prev = host_sl
+          yield (key_value(int(key)), img)
         else:
           out = np.zeros(labels.shape, dtype=np.float32, order=order)
-          out[mask] = dt[mask]
-          yield (key, out)
+          out[host_sl] = host_sub
+          yield (key_value(int(key)), out)
 
   return ImageIterator()
-
-
-def each_cuda(labels, dt):
-  """Device-resident `each`: yields (label, dt masked to that label) as torch CUDA tensors, so the
-  per-label images never cross PCIe."""
-  import torch
-  keys = [int(k) for k in torch.unique(labels).tolist() if k != 0]
-  zero = torch.zeros((), dtype=dt.dtype, device=dt.device)
-  for key in keys:
-    yield key, torch.where(labels == key, dt, zero)
 
 
 def release():

@@ -6,6 +6,7 @@
 // passes are stream-ordered kernel launches.  No CPU fallback exists in this file.
 #include "edt_host.h"
 #include "edt_voxel_graph.cuh"
+#include "edt_each.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -823,6 +824,81 @@ int edtb200_slab_face_fixup(const void* labels_dev, int label_bytes, int64_t sx,
     case 2: face_fixup_kernel<2><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(labels_dev), f_dev, plane, (int)sz, high_face, halo, w2, static_cast<const uint16_t*>(nb_label_dev), nb_m_dev, nb_f_dev, kflags, inexact_dev); break;
     case 4: face_fixup_kernel<4><<<blocks, 256, 0, stream>>>(static_cast<const uint32_t*>(labels_dev), f_dev, plane, (int)sz, high_face, halo, w2, static_cast<const uint32_t*>(nb_label_dev), nb_m_dev, nb_f_dev, kflags, inexact_dev); break;
     default: face_fixup_kernel<8><<<blocks, 256, 0, stream>>>(static_cast<const uint64_t*>(labels_dev), f_dev, plane, (int)sz, high_face, halo, w2, static_cast<const uint64_t*>(nb_label_dev), nb_m_dev, nb_f_dev, kflags, inexact_dev); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int edtb200_label_stats(const void* labels_dev, int label_bytes, const float* dt_dev, int64_t sx, int64_t sy,
+                        int64_t sz, int capacity, unsigned long long* keys_dev, unsigned long long* count_dev,
+                        float* max_dev, long long* argmax_dev, int* box_dev, int* overflow_dev, int device,
+                        void* stream_v) {
+  using namespace edtb200;
+  int rc = check_dims(label_bytes, 3, sx, sy, sz);
+  if (rc) return rc;
+  if (capacity < 2 || (capacity & (capacity - 1))) return fail(EDTB200_EINVAL, "capacity must be a power of two");
+  if (!labels_dev || !dt_dev || !keys_dev || !count_dev || !max_dev || !argmax_dev || !box_dev || !overflow_dev)
+    return fail(EDTB200_EINVAL, "null pointer");
+  if (sx > 0x7fffffff || sy > 0x7fffffff || sz > 0x7fffffff) return fail(EDTB200_ELIMIT, "axis too long");
+  DeviceGuard restore_device;
+  DeviceCache* dc = nullptr;
+  rc = probe(device, &dc);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  LabelTable t;
+  t.keys = keys_dev; t.count = count_dev; t.maxbits = reinterpret_cast<unsigned int*>(max_dev);
+  t.argmax = argmax_dev; t.box = box_dev; t.capacity = capacity; t.overflow = overflow_dev;
+  label_table_init_kernel<<<(capacity + 255) / 256, 256, 0, stream>>>(t);
+  CUDA_TRY(cudaMemsetAsync(overflow_dev, 0, sizeof(int), stream));
+  const int64_t total = sx * sy * sz;
+  if (total > 0) {
+    const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)dc->sm_count * 16);
+    switch (label_bytes) {
+#define EDT_STATS(B, T)                                                                                       \
+      case B:                                                                                                 \
+        label_stats_kernel<B><<<blocks, 256, 0, stream>>>(static_cast<const T*>(labels_dev), dt_dev, total,   \
+                                                          (int)sx, (int)sy, t);                               \
+        label_argmax_kernel<B><<<blocks, 256, 0, stream>>>(static_cast<const T*>(labels_dev), dt_dev, total, t); \
+        break;
+      EDT_STATS(1, uint8_t) EDT_STATS(2, uint16_t) EDT_STATS(4, uint32_t)
+      default:
+        label_stats_kernel<8><<<blocks, 256, 0, stream>>>(static_cast<const uint64_t*>(labels_dev), dt_dev, total,
+                                                          (int)sx, (int)sy, t);
+        label_argmax_kernel<8><<<blocks, 256, 0, stream>>>(static_cast<const uint64_t*>(labels_dev), dt_dev, total, t);
+#undef EDT_STATS
+    }
+  }
+  label_table_finish_kernel<<<(capacity + 255) / 256, 256, 0, stream>>>(t);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int edtb200_label_extract(const void* labels_dev, int label_bytes, const float* dt_dev, int64_t sx, int64_t sy,
+                          int64_t sz, unsigned long long key, const int* box, int erase, float* out_dev,
+                          int device, void* stream_v) {
+  using namespace edtb200;
+  int rc = check_dims(label_bytes, 3, sx, sy, sz);
+  if (rc) return rc;
+  if (!labels_dev || !dt_dev || !out_dev) return fail(EDTB200_EINVAL, "null pointer");
+  if (sx > 0x7fffffff || sy > 0x7fffffff || sz > 0x7fffffff) return fail(EDTB200_ELIMIT, "axis too long");
+  int b[6] = {0, 0, 0, (int)sx - 1, (int)sy - 1, (int)sz - 1};
+  if (box) for (int i = 0; i < 6; ++i) b[i] = box[i];
+  if (b[0] < 0 || b[1] < 0 || b[2] < 0 || b[3] >= sx || b[4] >= sy || b[5] >= sz)
+    return fail(EDTB200_EINVAL, "box outside the volume");
+  if (b[3] < b[0] || b[4] < b[1] || b[5] < b[2]) return 0;             // empty box
+  DeviceGuard restore_device;
+  DeviceCache* dc = nullptr;
+  rc = probe(device, &dc);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int bx = b[3] - b[0] + 1, by = b[4] - b[1] + 1, bz = b[5] - b[2] + 1;
+  const int64_t rows = (int64_t)by * bz;
+  const unsigned blocks = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)dc->sm_count * 16);
+  switch (label_bytes) {
+    case 1: label_extract_kernel<1><<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(labels_dev), dt_dev, out_dev, (int)sx, (int)sy, b[0], b[1], b[2], bx, by, bz, key, erase); break;
+    case 2: label_extract_kernel<2><<<blocks, 256, 0, stream>>>(static_cast<const uint16_t*>(labels_dev), dt_dev, out_dev, (int)sx, (int)sy, b[0], b[1], b[2], bx, by, bz, key, erase); break;
+    case 4: label_extract_kernel<4><<<blocks, 256, 0, stream>>>(static_cast<const uint32_t*>(labels_dev), dt_dev, out_dev, (int)sx, (int)sy, b[0], b[1], b[2], bx, by, bz, key, erase); break;
+    default: label_extract_kernel<8><<<blocks, 256, 0, stream>>>(static_cast<const uint64_t*>(labels_dev), dt_dev, out_dev, (int)sx, (int)sy, b[0], b[1], b[2], bx, by, bz, key, erase); break;
   }
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -673,12 +673,13 @@ struct HullWalk {
 // the hull -- at a fixed row the candidate values are unimodal.
 template <int TX>
 __device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, uint32_t cflagcol, int lo, int a, int b,
-                                           int n, float w2f, bool border_lo, bool border_hi, bool background) {
+                                           int n, float w2f, bool border_lo, bool border_hi, bool background,
+                                           bool all_const) {
   const float inf = __int_as_float(0x7f800000);
   w.a = a; w.b = b;
   w.lo_b = a > 0 || border_lo; w.hi_b = b < n || border_hi;
   w.bg = background;
-  w.cst = run_is_constant<TX>(ln, cflagcol, a, b);
+  w.cst = all_const || run_is_constant<TX>(ln, cflagcol, a, b);
   w.v = w.v1 = -1; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
   if (w.cst) return;
   int v = prev_vertex<TX>(ln, lo + 1, a);
@@ -893,7 +894,9 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           if (ent_mask && !(noncst & ent_mask)) { cflags |= 1u; if (ln.fval(i0) < inf) hb |= ent_mask; }
           if (lea_mask && !(noncst & lea_mask)) { cflags |= 2u; if (ln.fval(i0 + s2) < inf) hb |= lea_mask; }
           sts_u8(cflagcol + (uint32_t)c * TX, cflags);
-          any_cross = 1;
+          any_cross |= 1;
+          // bit 1: a crossing run that is not constant here, or across the boundary below
+          if ((noncst & cross_mask) || (entering && ln.fval(i0) != ln.fval(i0 - 1))) any_cross |= 2;
         }
         // (1c) hulls of the non-constant segments
         if (noncst) hb = build_hull_rows<TX>(ln, i0, noncst, starts, w2d, hb);
@@ -907,6 +910,9 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
     }
   }
   if (!__syncthreads_or(any_cross)) return;                // every run was finished inside its chunk
+  // every crossing run of the tile constant (blocky labels, solid objects along this axis)?  Then
+  // nothing needs stitching and stage 3 writes min(f, border terms) without looking at any hull.
+  const bool all_const = !__syncthreads_or(any_cross & 2);
 
   // ============ stage 2: stitch the hulls of runs that cross chunk boundaries ============
   // Divide and conquer over the chunks: at level l the groups of 2^(l-1) chunks left and right
@@ -918,6 +924,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   // B's first while it is hidden by (A's top, B's second), until neither applies.
   int levels = 0;
   while ((1 << levels) < nchunks) ++levels;
+  if (all_const) levels = 0;
   for (int lev = 1; lev <= levels; ++lev) {
     const int half = 1 << (lev - 1);
     if (live) {
@@ -1019,7 +1026,8 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           } else {
             b = min(n, i0 + 32);
           }
-          walk_begin<TX>(w, ln, cflagcol, i, a, b, n, w2, border_lo != 0, border_hi != 0, (wzero >> r) & 1u);
+          walk_begin<TX>(w, ln, cflagcol, i, a, b, n, w2, border_lo != 0, border_hi != 0, (wzero >> r) & 1u,
+                         all_const);
         }
         float best = inf;
         if (w.cst) {

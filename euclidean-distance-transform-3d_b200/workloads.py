@@ -3,7 +3,8 @@
 Used by bench.py (the `workloads` array), tools/perf_matrix.py and the GPU tests, so that all of
 them time and check the same volumes.  Every generator is seeded and returns a C-contiguous
 (z, y, x) torch CUDA tensor -- x fastest, the layout the kernels work in -- together with the
-anisotropy in (x, y, z) order and the black_border flag of the configuration it stands for.
+anisotropy per ARRAY axis, i.e. (w_z, w_y, w_x) as `edt_cuda` takes it, and the black_border flag
+of the configuration it stands for.
 
   cfg2     BASELINE configs[1]: iid labels 0..255, uint32, (1,1,1)        (runs of length ~1)
   cfg2b    32^3 constant blocks of random labels, uint32                  (blocky segmentation)
@@ -20,7 +21,7 @@ NAMES = ("cfg2", "cfg2b", "blocks8", "cfg3", "balls", "voronoi", "ones_nobb")
 
 
 def generate(name, n, device, nz=None):
-  """-> (labels[nz, n, n], anisotropy (wx, wy, wz), black_border).  nz defaults to n."""
+  """-> (labels[nz, n, n], anisotropy (w_z, w_y, w_x), black_border).  nz defaults to n."""
   nz = n if nz is None else nz
   g = torch.Generator(device=device)
   g.manual_seed(0)
@@ -32,7 +33,7 @@ def generate(name, n, device, nz=None):
     big = small.repeat_interleave(k, 0).repeat_interleave(k, 1).repeat_interleave(k, 2)
     return big[:nz, :n, :n].contiguous(), (1, 1, 1), False
   if name == "cfg3":
-    return torch.ones((nz, n, n), dtype=torch.uint8, device=device), (6, 6, 30), True
+    return torch.ones((nz, n, n), dtype=torch.uint8, device=device), (30, 6, 6), True
   if name == "ones_nobb":
     return torch.ones((nz, n, n), dtype=torch.uint8, device=device), (1, 1, 1), False
   if name in ("balls", "voronoi"):

@@ -169,6 +169,29 @@ int edtb200_slab_face_fixup(const void *labels_dev, int label_bytes,
                             const float *nb_f_dev, float *f_dev, int *inexact_dev,
                             int device, void *stream);
 
+/* Per-label views of a finished transform, on the device: the reference's `edt.each`
+ * (src/edt.pyx:951-994: one masked distance image per label, built from run lists,
+ * src/edt_voxel_graph.hpp:238-310) for labels and distances that are already resident on the GPU.
+ *
+ * edtb200_label_stats : ONE pass over (labels, dt) fills an open-addressing table of `capacity`
+ *     slots (a power of two, at least twice the number of distinct labels): keys_dev[s] = label
+ *     (0 = empty slot; label 0 is background and skipped), count_dev[s] = its voxels,
+ *     max_dev[s] = its largest distance, argmax_dev[s] = the smallest linear index (x fastest)
+ *     where that maximum is attained, box_dev[6*s..] = bounding box x0 y0 z0 x1 y1 z1 (inclusive).
+ *     *overflow_dev is raised when the table was too small (repeat with a larger capacity).
+ * edtb200_label_extract : out = (labels == key) ? dt : 0 inside `box` (6 host ints as above, NULL =
+ *     whole volume), nothing outside it is touched -- the equivalent of transfer_run_voxels on a
+ *     blank image; erase != 0 zeroes the box instead (the reference's erase()).
+ * All pointers except `box` are device pointers on `device`; asynchronous on `stream`. */
+int edtb200_label_stats(const void *labels_dev, int label_bytes, const float *dt_dev,
+                        int64_t sx, int64_t sy, int64_t sz, int capacity,
+                        unsigned long long *keys_dev, unsigned long long *count_dev, float *max_dev,
+                        long long *argmax_dev, int *box_dev, int *overflow_dev, int device, void *stream);
+
+int edtb200_label_extract(const void *labels_dev, int label_bytes, const float *dt_dev,
+                          int64_t sx, int64_t sy, int64_t sz, unsigned long long key, const int *box,
+                          int erase, float *out_dev, int device, void *stream);
+
 /* Measurement hooks (used by bench.py): with profiling enabled on the calling thread, every
  * edtb200_transform records CUDA events around its axis passes on the transform's stream into a
  * ring of 256 slots -- nothing synchronises inside a timed loop.  edtb200_pass_ms(k, ms) waits
