@@ -91,9 +91,10 @@ def test_label_views(edt):
   assert edt._label_view(np.zeros(3, np.float16)) is None
 
 
+@pytest.mark.gpu
 def test_each_mirrors_reference_contract(edt):
   """edt.each (src/edt.pyx:951-994, automated_test.py:831-856): per-label images from one
-  multi-label transform; pure host post-processing, so it is testable without a GPU."""
+  multi-label transform; the images are drawn on the device (csrc/edt_each.cuh)."""
   rng = np.random.default_rng(8)
   labels = rng.integers(0, 6, (9, 8, 7)).astype(np.uint32)
   dt = rng.random((9, 8, 7)).astype(np.float32) * (labels != 0)
