@@ -89,6 +89,11 @@ def _lib():
   lib.edtb200_profile_passes.restype = ci
   lib.edtb200_pass_ms.argtypes = [ci, vp]
   lib.edtb200_pass_ms.restype = ci
+  lib.edtb200_slab_stage_bytes.argtypes = [i64, i64, ci, ci]
+  lib.edtb200_slab_stage_bytes.restype = i64
+  lib.edtb200_slab_step.argtypes = [vp, ci, i64, i64, i64, f32, f32, f32, ci, ci, ci, ci, vp, ci, vp, vp, vp,
+                                    ctypes.c_uint64, vp, ci, vp]
+  lib.edtb200_slab_step.restype = ci
   lib.edtb200_label_stats.argtypes = [vp, ci, vp, i64, i64, i64, ci, vp, vp, vp, vp, vp, vp, ci, vp]
   lib.edtb200_label_stats.restype = ci
   lib.edtb200_label_extract.argtypes = [vp, ci, vp, i64, i64, i64, ctypes.c_uint64, vp, ci, vp, ci, vp]

@@ -7,11 +7,13 @@
 #include "edt_host.h"
 #include "edt_voxel_graph.cuh"
 #include "edt_each.cuh"
+#include "edt_slab.cuh"
 
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -413,6 +415,32 @@ void mark_pass(int idx, cudaStream_t stream) {
   g_pass_marks[slot] = idx;
 }
 
+// NVTX ranges edt.x / edt.y / edt.z / edt.halo.*  around the launches, so
+// that an Nsight Systems timeline names the passes.  libnvToolsExt is looked up at run time
+// (dlopen), so it is not a dependency; without it the calls do nothing.
+typedef int (*NvtxPushFn)(const char*);
+typedef int (*NvtxPopFn)(void);
+NvtxPushFn g_nvtx_push = nullptr;
+NvtxPopFn g_nvtx_pop = nullptr;
+std::once_flag g_nvtx_once;
+
+void nvtx_init() {
+  std::call_once(g_nvtx_once, [] {
+    if (getenv("EDTB200_NO_NVTX")) return;
+    const char* names[] = {"libnvToolsExt.so.1", "libnvToolsExt.so", nullptr};
+    for (int i = 0; names[i]; ++i) {
+      void* h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+      if (!h) continue;
+      g_nvtx_push = reinterpret_cast<NvtxPushFn>(dlsym(h, "nvtxRangePushA"));
+      g_nvtx_pop = reinterpret_cast<NvtxPopFn>(dlsym(h, "nvtxRangePop"));
+      if (g_nvtx_push && g_nvtx_pop) return;
+      g_nvtx_push = nullptr; g_nvtx_pop = nullptr;
+    }
+  });
+}
+void nvtx_push(const char* name) { nvtx_init(); if (g_nvtx_push) g_nvtx_push(name); }
+void nvtx_pop() { if (g_nvtx_pop) g_nvtx_pop(); }
+
 // All passes of one transform on device-resident buffers.
 int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_t sy, int64_t sz,
                float wx, float wy, float wz, int border, int flags, float* f,
@@ -431,18 +459,42 @@ int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_
   // but X 0.180 -> 0.350 ms at 512^3 uint32.)
   int rc = 0;
   const edtb200::LineGeom gy = geom_for_axis(1, sx, sy, sz), gz = geom_for_axis(2, sx, sy, sz);
+  // EDT_B200_VERBOSE=1: per-pass device times of every transform on stderr.
+  // The dump needs the passes to have finished, so a verbose transform synchronises its stream.
+  static const bool verbose = getenv("EDT_B200_VERBOSE") != nullptr && atoi(getenv("EDT_B200_VERBOSE")) != 0;
+  const bool profile_was = g_profile;
+  if (verbose) g_profile = true;
   mark_pass(0, stream);
+  nvtx_push("edt.x");
   rc = dispatch_first(label_bytes, labels, f, sy * sz, sx, wx, border, zero_label | (ndim == 1 ? epilogue : 0), dc,
                       stream);
+  nvtx_pop();
   mark_pass(1, stream);
   if (!rc && ndim >= 2) {
+    nvtx_push("edt.y");
     rc = dispatch_later(label_bytes, labels, f, gy, wy, border, border, ndim == 2 ? epilogue : 0, dc, stream,
                         /*pdl=*/true);
+    nvtx_pop();
     mark_pass(2, stream);
   }
   if (!rc && ndim >= 3) {
+    nvtx_push("edt.z");
     rc = dispatch_later(label_bytes, labels, f, gz, wz, border, border, epilogue, dc, stream, /*pdl=*/true);
+    nvtx_pop();
     mark_pass(3, stream);
+  }
+  if (verbose) {
+    g_profile = profile_was;
+    float ms[3] = {0.0f, 0.0f, 0.0f};
+    if (!rc && edtb200_pass_ms(0, ms) == 0) {
+      const double nvox = (double)sx * (double)sy * (double)sz;
+      const double total = ms[0] + ms[1] + ms[2];
+      fprintf(stderr, "[edt_b200] %lldx%lldx%lld L=%d  x %.3f ms  y %.3f ms  z %.3f ms  total %.3f ms  "
+                      "%.0f Mvox/s  %.0f GB/s algorithmic\n",
+              (long long)sx, (long long)sy, (long long)sz, label_bytes, ms[0], ms[1], ms[2], total,
+              total > 0 ? nvox / total / 1e3 : 0.0,
+              total > 0 ? nvox * (3.0 * label_bytes + 20.0) / total / 1e6 : 0.0);
+    }
   }
   return rc;
 }
@@ -826,6 +878,105 @@ int edtb200_slab_face_fixup(const void* labels_dev, int label_bytes, int64_t sx,
     default: face_fixup_kernel<8><<<blocks, 256, 0, stream>>>(static_cast<const uint64_t*>(labels_dev), f_dev, plane, (int)sz, high_face, halo, w2, static_cast<const uint64_t*>(nb_label_dev), nb_m_dev, nb_f_dev, kflags, inexact_dev); break;
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int64_t edtb200_slab_stage_bytes(int64_t sx, int64_t sy, int label_bytes, int halo) {
+  if (sx <= 0 || sy <= 0 || halo < 1 || halo > 254 ||
+      !(label_bytes == 1 || label_bytes == 2 || label_bytes == 4 || label_bytes == 8))
+    return -1;
+  return (int64_t)edtb200::slab_stage_layout(sx * sy, label_bytes, halo).total_bytes;
+}
+
+int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
+                      float wx, float wy, float wz, int black_border, int has_lo, int has_hi, int flags,
+                      float* f_dev, int halo, void* sym_self, void* sym_lo, void* sym_hi,
+                      unsigned long long step, int* status_dev, int device, void* stream_v) {
+  using namespace edtb200;
+  int rc = check_dims(label_bytes, 3, sx, sy, sz);
+  if (rc) return rc;
+  if (halo < 1 || halo > 254) return fail(EDTB200_EINVAL, "halo must be in 1..254");
+  if (sz <= halo && (has_lo || has_hi)) return fail(EDTB200_EINVAL, "the slab must be deeper than the halo");
+  if (!labels_dev || !f_dev || !sym_self || !status_dev) return fail(EDTB200_EINVAL, "null pointer");
+  if ((has_lo && !sym_lo) || (has_hi && !sym_hi)) return fail(EDTB200_EINVAL, "missing neighbour buffer");
+  if (step == 0) return fail(EDTB200_EINVAL, "steps are counted from 1");
+  DeviceGuard restore_device;
+  DeviceCache* dc = nullptr;
+  rc = probe(device, &dc);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int border = black_border != 0;
+  const int zero_label = (flags & EDTB200_SIGNED) ? kZeroLabel : 0;
+  const int epilogue = ((flags & EDTB200_SQRT) ? kSqrt : 0) | ((flags & EDTB200_SIGNED) ? kNegate : 0);
+  const edtb200::LineGeom gy = geom_for_axis(1, sx, sy, sz), gz = geom_for_axis(2, sx, sy, sz);
+
+  // X and Y passes: slab-local
+  nvtx_push("edt.x");
+  rc = dispatch_first(label_bytes, labels_dev, f_dev, sy * sz, sx, wx, border, zero_label, *dc, stream);
+  nvtx_pop();
+  if (rc) return rc;
+  nvtx_push("edt.y");
+  rc = dispatch_later(label_bytes, labels_dev, f_dev, gy, wy, border, border, 0, *dc, stream, /*pdl=*/true);
+  nvtx_pop();
+  if (rc) return rc;
+
+  const int64_t plane = sx * sy;
+  const SlabStageLayout L = slab_stage_layout(plane, label_bytes, halo);
+  unsigned char* self = static_cast<unsigned char*>(sym_self);
+  unsigned char* lo = static_cast<unsigned char*>(sym_lo);
+  unsigned char* hi = static_cast<unsigned char*>(sym_hi);
+  const int parity = (int)(step & 1ull);
+  const dim3 grid((unsigned)((plane + 255) / 256), 2);
+  if (has_lo || has_hi) {
+    nvtx_push("edt.halo.stage");
+    unsigned char* set = self + (size_t)parity * L.set_bytes;
+    // I am the HIGH neighbour of the rank below me and the LOW neighbour of the rank above me
+    unsigned long long* flag_in_lo_peer = has_lo ? reinterpret_cast<unsigned long long*>(lo + L.flag_from_hi) : nullptr;
+    unsigned long long* flag_in_hi_peer = has_hi ? reinterpret_cast<unsigned long long*>(hi + L.flag_from_lo) : nullptr;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(self + L.counter);
+#define EDT_STAGE(B, T)                                                                                          \
+    slab_stage_kernel<B><<<grid, 256, 0, stream>>>(static_cast<const T*>(labels_dev), f_dev, plane, (int)sz, halo, \
+                                                   has_lo, has_hi, set, L, step, flag_in_lo_peer, flag_in_hi_peer, counter)
+    switch (label_bytes) {
+      case 1: EDT_STAGE(1, uint8_t); break;
+      case 2: EDT_STAGE(2, uint16_t); break;
+      case 4: EDT_STAGE(4, uint32_t); break;
+      default: EDT_STAGE(8, uint64_t); break;
+    }
+#undef EDT_STAGE
+    CUDA_TRY(cudaGetLastError());
+    nvtx_pop();
+  }
+
+  // Z pass on the slab, interior faces open
+  nvtx_push("edt.z");
+  rc = dispatch_later(label_bytes, labels_dev, f_dev, gz, wz, border && !has_lo, border && !has_hi, epilogue, *dc,
+                      stream, /*pdl=*/false);
+  nvtx_pop();
+  if (rc) return rc;
+
+  if (has_lo || has_hi) {
+    nvtx_push("edt.halo.fixup");
+    const int kflags = epilogue | zero_label;
+    const float w2 = wz * wz;
+    const unsigned char* set_lo = has_lo ? lo + (size_t)parity * L.set_bytes : nullptr;
+    const unsigned char* set_hi = has_hi ? hi + (size_t)parity * L.set_bytes : nullptr;
+    const unsigned long long* flag_from_lo = reinterpret_cast<const unsigned long long*>(self + L.flag_from_lo);
+    const unsigned long long* flag_from_hi = reinterpret_cast<const unsigned long long*>(self + L.flag_from_hi);
+#define EDT_FIXUP(B, T)                                                                                          \
+    slab_fixup_kernel<B><<<grid, 256, 0, stream>>>(static_cast<const T*>(labels_dev), f_dev, plane, (int)sz, halo, w2, \
+                                                   has_lo, has_hi, set_lo, set_hi, L, step, flag_from_lo, flag_from_hi, \
+                                                   kflags, status_dev)
+    switch (label_bytes) {
+      case 1: EDT_FIXUP(1, uint8_t); break;
+      case 2: EDT_FIXUP(2, uint16_t); break;
+      case 4: EDT_FIXUP(4, uint32_t); break;
+      default: EDT_FIXUP(8, uint64_t); break;
+    }
+#undef EDT_FIXUP
+    CUDA_TRY(cudaGetLastError());
+    nvtx_pop();
+  }
   return 0;
 }
 

@@ -87,6 +87,19 @@ class CudaPasses:
                                             f.data_ptr(), self.device.index, self._stream()))
 
 
+  def slab_step(self, labels, f, w_xyz, black_border, has_lo, has_hi, sqrt, signed, halo, sym_self, sym_lo, sym_hi,
+                step, status):
+    """One fused slab step (edtb200_slab_step): X, Y, stage faces, Z, fix-up, on the current stream."""
+    sz, sy, sx = labels.shape
+    nbytes = _torch_label_bytes(torch)[labels.dtype]
+    flags = (FLAG_SQRT if sqrt else 0) | (FLAG_SIGNED if signed else 0)
+    self._check(self.lib.edtb200_slab_step(labels.data_ptr(), nbytes, sx, sy, sz, float(w_xyz[0]), float(w_xyz[1]),
+                                           float(w_xyz[2]), int(bool(black_border)), int(bool(has_lo)),
+                                           int(bool(has_hi)), flags, f.data_ptr(), int(halo),
+                                           ctypes.c_void_p(sym_self), ctypes.c_void_p(sym_lo or None),
+                                           ctypes.c_void_p(sym_hi or None), ctypes.c_uint64(step),
+                                           status.data_ptr(), self.device.index, self._stream()))
+
   def face_runs(self, labels, high_face, halo, signed, overflow, out=None):
     """uint8 (sy, sx) run lengths at one face; raises the device int `overflow` when too long."""
     sz, sy, sx = labels.shape
@@ -129,76 +142,71 @@ def _all_to_all(send_chunks, recv_chunks, group):
 
 
 class PeerHalo:
-  """Face staging buffers in CUDA symmetric memory (torch.distributed._symmetric_memory): every
-  rank publishes, per step, its two face planes of labels, its face run lengths and its first /
-  last `halo` planes of Y-pass distances in a buffer that its neighbours map over NVLink, and
-  the neighbours' `face_fixup_kernel` READS them in place -- only the rows it actually needs
-  (typically one or two planes), instead of receiving all `halo` planes through NCCL.
-  Two parity sets + pairwise put_signal / wait_signal order writers and readers across steps:
-  a rank overwrites set p at step k+2 only after it has seen its neighbours' step-(k+1) signal,
-  which they issue after their step-k fix-up (the last reader of set p).
-
+  """Face staging buffer in CUDA symmetric memory (torch.distributed._symmetric_memory) for the
+  fused slab step `edtb200_slab_step` (csrc/edt_slab.cuh): every rank publishes, per step, its two
+  face planes of labels, its face run lengths and its first / last `halo` planes of Y-pass
+  distances in its own buffer, raises a flag word in each neighbour's buffer (a remote NVLink
+  store), and the neighbours' fix-up kernel READS the staged faces in place over NVLink -- only
+  the rows it actually needs (typically one or two planes).  Two staging sets alternate by step
+  parity; the flag words order writers and readers across steps, no host call is involved.
   Creating one is a collective call over `group`; reuse it for every transform of the same
-  (sy, sx, label dtype, halo)."""
+  (sy, sx, label width, halo)."""
 
-  def __init__(self, device, sy, sx, label_dtype, halo=32, group=None):
+  def __init__(self, device, sy, sx, label_dtype, halo=8, group=None):
     import torch.distributed._symmetric_memory as symm_mem
     self.group = group if group is not None else dist.group.WORLD
     self.rank = dist.get_rank(group)
     self.world = dist.get_world_size(group)
     self.halo, self.sy, self.sx = int(halo), int(sy), int(sx)
-    esz = torch.empty((), dtype=label_dtype).element_size()
-    self.esz = esz
-    plane = self.sy * self.sx
-    pad = lambda n: (n + 255) // 256 * 256
-    self.layout, off = {}, 0
-    for name, nbytes in (("f_lo", self.halo * plane * 4), ("f_hi", self.halo * plane * 4),
-                         ("lab_lo", plane * esz), ("lab_hi", plane * esz), ("m_lo", plane), ("m_hi", plane)):
-      self.layout[name] = (off, nbytes)
-      off += pad(nbytes)
-    self.set_bytes = off
-    self.buf = symm_mem.empty(2 * self.set_bytes, dtype=torch.uint8, device=device)
+    self.esz = torch.empty((), dtype=label_dtype).element_size()
+    lib = _lib()
+    self.nbytes = int(lib.edtb200_slab_stage_bytes(self.sx, self.sy, self.esz, self.halo))
+    if self.nbytes <= 0:
+      raise ValueError("bad staging geometry")
+    self.buf = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=device)
+    self.buf.zero_()                                   # flag words and the CTA counter start at 0
+    torch.cuda.synchronize(device)
     self.hdl = symm_mem.rendezvous(self.buf, self.group)
+    dist.barrier(group=self.group)                     # every rank's buffer is zeroed before any step
     self.step = 0
-    self._flat = {}
-    self._views = {}
+    self._peers = {}
+    self.status = torch.zeros(1, dtype=torch.int32, device=device)
 
   def matches(self, sy, sx, label_dtype, halo):
     esz = torch.empty((), dtype=label_dtype).element_size()
     return (self.sy, self.sx, self.esz, self.halo) == (int(sy), int(sx), esz, int(halo))
 
-  def views(self, rank, parity):
-    """Typed views of `rank`'s staging set `parity` (own memory or a peer's, mapped over NVLink)."""
-    if (rank, parity) in self._views:
-      return self._views[(rank, parity)]
-    if rank not in self._flat:
-      self._flat[rank] = self.buf if rank == self.rank else \
-          self.hdl.get_buffer(rank, (2 * self.set_bytes,), torch.uint8, 0)
-    flat = self._flat[rank]
-    base = parity * self.set_bytes
-    out = {}
-    for name, (off, nbytes) in self.layout.items():
-      raw = flat[base + off: base + off + nbytes]
-      if name.startswith("f_"):
-        out[name] = raw.view(torch.float32).reshape(self.halo, self.sy, self.sx)
-      elif name.startswith("lab_"):
-        out[name] = raw.reshape(self.sy, self.sx * self.esz)        # raw label bytes
-      else:
-        out[name] = raw.reshape(self.sy, self.sx)
-    self._views[(rank, parity)] = out
-    return out
+  def peer_ptr(self, rank):
+    """Device address of `rank`'s staging buffer as mapped into this process (0 if out of range)."""
+    if rank < 0 or rank >= self.world:
+      return 0
+    if rank == self.rank:
+      return self.buf.data_ptr()
+    if rank not in self._peers:
+      self._peers[rank] = self.hdl.get_buffer(rank, (self.nbytes,), torch.uint8, 0)
+    return self._peers[rank].data_ptr()
 
 
-def check_verdicts(verdicts):
-  """True if every deferred halo verdict (info["verdict"] of slab_transform) is clean."""
+def check_verdicts(verdicts, group=None):
+  """True if every deferred halo verdict (info["verdict"] of slab_transform) is clean on every
+  rank.  Verdicts deferred with defer_check="local" are still per-rank device flags: they are
+  combined here with ONE all-reduce for the whole batch."""
   worst = 0
+  local = [flag for flag, work in verdicts if work is None]
   for flag, work in verdicts:
-    work.wait()
-    worst = max(worst, int(flag.item()))
+    if work is not None:
+      work.wait()
+      worst = max(worst, int(flag.item()))
+  if local:
+    combined = torch.stack([f.reshape(()) for f in local]).max().reshape(1)
+    dist.all_reduce(combined, op=dist.ReduceOp.MAX, group=group)
+    worst = max(worst, int(combined.item()))
+  if worst >= 2:
+    raise EDTError("slab step: a neighbouring rank never published its faces (time-out in the fix-up kernel)")
   return worst == 0
 
 
-def make_peer_halo(device, sy, sx, label_dtype, halo=32, group=None):
+def make_peer_halo(device, sy, sx, label_dtype, halo=8, group=None):
   """PeerHalo, or (None, reason) when symmetric memory is unavailable (then slab_transform uses
   the NCCL send/recv exchange).  Collective over `group`; returns (peer_halo, reason)."""
   try:
@@ -228,6 +236,9 @@ def _peer(group, r):
 
 
 _HALO_HINT = {}      # (group, plane shape) -> halo depth that was last needed there
+DEFAULT_HALO = 8     # rows of the neighbours' distances staged per face; exact whenever the distances
+                     # at the faces stay below 8 * w_z (the fix-up checks it and the step is repeated
+                     # with 32, then 128 rows, then by transposition when they do not)
 
 
 def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False, *, sqrt=False,
@@ -242,8 +253,8 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   method: "auto" (halo exchange; when its verdict says it was not exact for this volume the step
   is repeated with a four times deeper halo, up to 128 rows, then with transpose), "halo" (raise if
   not exact), "transpose".
-  halo: rows of the neighbours' distances a rank can see (1..254).  None = 32, or the depth the
-  last "auto" call on the same group and plane shape ended up needing.  `info`, if a dict, receives {"method": ...}.
+  halo: rows of the neighbours' distances a rank can see (1..254).  None = 8 (DEFAULT_HALO), or the
+  depth the last "auto" call on the same group and plane shape ended up needing.  `info`, if a dict, receives {"method": ...}.
   depths: slab depth of every rank, if the caller knows them (saves one small all-reduce per call).
   peer_halo: a PeerHalo (symmetric-memory staging); the fix-up then reads the neighbours' faces
   directly over NVLink instead of receiving `halo` planes through NCCL send/recv.  "auto" (the
@@ -255,7 +266,9 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   one host synchronisation.
   With defer_check=True the call returns without reading it and puts it in info["verdict"]
   (call `check_verdicts` on a batch of them later); a non-zero verdict means the result must be
-  recomputed with method="transpose".
+  recomputed with a deeper halo or method="transpose".  defer_check="local" also skips the
+  all-reduce: the call then contains no collective at all and `check_verdicts` combines the
+  ranks' flags once for the whole batch.
   """
   world = dist.get_world_size(group)
   rank = dist.get_rank(group)
@@ -268,7 +281,7 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     if isinstance(peer_halo, PeerHalo):
       halo = peer_halo.halo                  # an explicit staging buffer fixes the depth
     else:
-      halo = _HALO_HINT.get(hint_key, 32) if method == "auto" else 32
+      halo = _HALO_HINT.get(hint_key, DEFAULT_HALO) if method == "auto" else DEFAULT_HALO
   marks = info.get("marks") if isinstance(info, dict) else None      # optional CUDA-event phase marks
 
   def mark(name):
@@ -300,24 +313,26 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   if isinstance(peer_halo, str):
     peer_halo = _auto_peer_halo(labels_local, sy, sx, halo, group) if (use_halo and peer_halo == "auto") else None
   m_lo = m_hi = None
+  fused = use_halo and peer_halo is not None
+  if fused and not peer_halo.matches(sy, sx, labels_local.dtype, halo):
+    raise ValueError("peer_halo was created for another plane shape / dtype / halo")
   if use_halo:
     overflow = torch.zeros(1, dtype=torch.int32, device=labels_local.device)    # hint only, not reduced
     inexact = torch.zeros(1, dtype=torch.int32, device=labels_local.device)
-    stage = None
-    if peer_halo is not None:
-      if not peer_halo.matches(sy, sx, labels_local.dtype, halo):
-        raise ValueError("peer_halo was created for another plane shape / dtype / halo")
-      parity = peer_halo.step & 1
-      peer_halo.step += 1
-      stage = peer_halo.views(rank, parity)
-    if rank > 0:
-      m_lo = passes.face_runs(labels_local, 0, halo, signed, overflow, out=stage["m_lo"] if stage else None)
-    if rank < world - 1:
-      m_hi = passes.face_runs(labels_local, 1, halo, signed, overflow, out=stage["m_hi"] if stage else None)
+    if not fused:
+      if rank > 0:
+        m_lo = passes.face_runs(labels_local, 0, halo, signed, overflow)
+      if rank < world - 1:
+        m_hi = passes.face_runs(labels_local, 1, halo, signed, overflow)
   mark("face_runs")
 
   def halo_verdict(result):
     """All-reduce the fix-up kernels' flag; hand it to the caller (deferred) or act on it."""
+    if defer_check == "local":               # no collective at all in this call
+      if info is None:
+        raise ValueError("defer_check needs an `info` dict to receive the verdict")
+      info["verdict"] = (inexact, None)
+      return result
     work = dist.all_reduce(inexact, op=dist.ReduceOp.MAX, group=group, async_op=True)
     if defer_check:
       if info is None:
@@ -325,6 +340,8 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
       info["verdict"] = (inexact, work)
       return result
     work.wait()
+    if int(inexact.item()) >= 2:
+      raise EDTError("slab step: a neighbouring rank never published its faces (time-out in the fix-up kernel)")
     if int(inexact.item()) == 0:
       if info is not None:
         info["halo"] = halo
@@ -334,7 +351,7 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     if method == "halo":
       raise EDTError("halo method is not exact here: a run goes on behind the %d halo rows of a neighbouring "
                      "slab and the distances at that face exceed the halo's reach" % halo)
-    deeper = min(4 * halo, 128)
+    deeper = min(4 * halo, 128)               # 8 -> 32 -> 128
     sub = info if info is not None else {}
     again = dict(sqrt=sqrt, signed=signed, group=group, passes=passes, info=sub, depths=depths)
     if deeper > halo and min(depths) > deeper:
@@ -345,6 +362,18 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     if remember and sub.get("method") == "halo":
       _HALO_HINT[hint_key] = sub["halo"]
     return out
+
+  if fused:
+    # ---- the whole step in ONE C call: X, Y, publish faces, Z, fix-up (csrc/edt_slab.cuh) ----
+    f = passes.empty_f32((zc, sy, sx))
+    peer_halo.step += 1
+    passes.slab_step(labels_local, f, (wx, wy, wz), black_border, rank > 0, rank < world - 1, sqrt, signed, halo,
+                     peer_halo.peer_ptr(rank), peer_halo.peer_ptr(rank - 1) if rank > 0 else 0,
+                     peer_halo.peer_ptr(rank + 1) if rank < world - 1 else 0, peer_halo.step, inexact)
+    mark("fused slab step")
+    if info is not None:
+      info["method"] = "halo"
+    return halo_verdict(f)
 
   # ---- X and Y passes: slab-local, no communication ----
   f = passes.empty_f32((zc, sy, sx))
@@ -364,34 +393,6 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
     raise EDTError("halo method needs more than one rank and slabs deeper than the halo (%d)" % halo)
   if info is not None:
     info["method"] = "halo" if use_halo else "transpose"
-
-  if use_halo and peer_halo is not None:
-    # ---- publish my faces in symmetric memory, signal the neighbours, Z pass, read theirs ----
-    stage["f_lo"].copy_(f[:halo])
-    stage["f_hi"].copy_(f[zc - halo:])
-    lab_bytes = labels_local.view(torch.uint8).reshape(zc, sy, sx * labels_local.element_size())
-    stage["lab_lo"].copy_(lab_bytes[0])
-    stage["lab_hi"].copy_(lab_bytes[zc - 1])
-    nbs = [nb for nb in (rank - 1, rank + 1) if 0 <= nb < world]
-    for nb in nbs:
-      peer_halo.hdl.put_signal(nb, parity)
-    mark("faces staged + signalled")
-    passes.pass_later(labels_local, f, 2, wz, black_border and rank == 0, black_border and rank == world - 1,
-                      sqrt=sqrt, negate=signed)
-    mark("z pass")
-    for nb in nbs:
-      peer_halo.hdl.wait_signal(nb, parity)
-    mark("neighbours ready")
-    if rank > 0:
-      nbv = peer_halo.views(rank - 1, parity)
-      passes.face_fixup(labels_local, f, 0, halo, wz, sqrt, signed, nbv["lab_hi"].view(labels_local.dtype),
-                        nbv["m_hi"], nbv["f_hi"], inexact)
-    if rank < world - 1:
-      nbv = peer_halo.views(rank + 1, parity)
-      passes.face_fixup(labels_local, f, 1, halo, wz, sqrt, signed, nbv["lab_lo"].view(labels_local.dtype),
-                        nbv["m_lo"], nbv["f_lo"], inexact)
-    mark("face fix-up (peer reads)")
-    return halo_verdict(f)
 
   if use_halo:
     # ---- one neighbour exchange: face labels, face run lengths, `halo` planes of distances ----

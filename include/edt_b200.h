@@ -169,6 +169,31 @@ int edtb200_slab_face_fixup(const void *labels_dev, int label_bytes,
                             const float *nb_f_dev, float *f_dev, int *inexact_dev,
                             int device, void *stream);
 
+/* One whole step of the Z-slab decomposition on this rank, device-resident, asynchronous on
+ * `stream`: X pass, Y pass, publication of this slab's faces to the neighbours, Z pass (interior
+ * faces open) and the fix-up that folds the neighbours' rows in -- five launches from ONE call, no
+ * host synchronisation, no collective.  The ranks meet only through flag words in a staging buffer
+ * that every rank allocates in CUDA symmetric memory (peer-mapped over NVLink):
+ *   sym_self        this rank's buffer, edtb200_slab_stage_bytes(sx, sy, label_bytes, halo) bytes,
+ *                   ZERO-FILLED once before the first step (all ranks, then a barrier)
+ *   sym_lo, sym_hi  the lower / upper neighbour's buffer as mapped into this process (NULL where
+ *                   has_lo / has_hi is 0)
+ *   step            1, 2, 3, ... the same on every rank; staging sets alternate by its parity
+ *   status_dev      device int, OR-ed with 1 when the halo was too shallow for this volume (a run
+ *                   goes on behind the neighbour's `halo` rows and the distances at the face exceed
+ *                   the halo's reach: repeat with a deeper halo or an exact method), and with 2
+ *                   when a neighbour never published the step (time-out)
+ * flags: EDTB200_SQRT / EDTB200_SIGNED as for edtb200_transform; black_border applies to the real
+ * volume faces only (z low face on the rank with has_lo == 0, z high face where has_hi == 0).
+ * This is what replaces the reference's single-address-space Z loop (src/edt.hpp:465-475) when
+ * the volume is spread over several GPUs. */
+int64_t edtb200_slab_stage_bytes(int64_t sx, int64_t sy, int label_bytes, int halo);
+
+int edtb200_slab_step(const void *labels_dev, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
+                      float wx, float wy, float wz, int black_border, int has_lo, int has_hi, int flags,
+                      float *f_dev, int halo, void *sym_self, void *sym_lo, void *sym_hi,
+                      unsigned long long step, int *status_dev, int device, void *stream);
+
 /* Per-label views of a finished transform, on the device: the reference's `edt.each`
  * (src/edt.pyx:951-994: one masked distance image per label, built from run lists,
  * src/edt_voxel_graph.hpp:238-310) for labels and distances that are already resident on the GPU.
