@@ -73,6 +73,8 @@ def _lib():
   lib.edtb200_device_count.restype = ci
   lib.edtb200_transform.argtypes = [vp, ci, ci, i64, i64, i64, f32, f32, f32, ci, ci, vp, ci, vp]
   lib.edtb200_transform.restype = ci
+  lib.edtb200_transform_multi.argtypes = [vp, ci, ci, i64, i64, i64, f32, f32, f32, ci, ci, vp, vp, ci]
+  lib.edtb200_transform_multi.restype = ci
   lib.edtb200_transform_batch.argtypes = [vp, vp, ci, ci, ci, i64, i64, i64, f32, f32, f32, ci, ci, ci]
   lib.edtb200_transform_batch.restype = ci
   lib.edtb200_transform_voxel_graph.argtypes = [vp, ci, vp, ci, i64, i64, i64, f32, f32, f32, ci, ci, vp, ci, vp]
@@ -164,6 +166,15 @@ def _transform_host(data, anisotropy, black_border, flags, device):
   (sx, sy, sz), (wx, wy, wz) = _x_fastest(data.shape, anisotropy, order == "F")
   out = np.empty(data.size, dtype=np.float32)
   lib = _lib()
+  if isinstance(device, (list, tuple, range)) or (isinstance(device, np.ndarray) and device.ndim == 1):
+    # several GPUs of this process share ONE host volume (edtb200_transform_multi): Z slabs for the
+    # X / Y passes, Y slabs for the Z pass, re-partitioned over NVLink; exact for any input
+    devs = [int(d) for d in device]
+    arr = (ctypes.c_int * len(devs))(*devs)
+    _check(lib.edtb200_transform_multi(
+      labels.ctypes.data, labels.dtype.itemsize, nd, sx, sy, sz, wx, wy, wz,
+      int(bool(black_border)), int(flags), out.ctypes.data, arr, len(devs)))
+    return out.reshape(data.shape, order=order)
   _check(lib.edtb200_transform(
     labels.ctypes.data, labels.dtype.itemsize, nd, sx, sy, sz, wx, wy, wz,
     int(bool(black_border)), int(flags), out.ctypes.data, int(device), None))
@@ -196,6 +207,8 @@ def _transform_voxel_graph_host(data, voxel_graph, anisotropy, black_border, fla
     return np.zeros(data.shape, dtype=np.float32, order=order)   # no branch in the reference either
   (sx, sy, sz), (wx, wy, wz) = _x_fastest(data.shape, anisotropy, order == "F")
   out = np.empty(data.size, dtype=np.float32)
+  if isinstance(device, (list, tuple)):
+    device = device[0]                      # the graph transform runs on one GPU
   _check(_lib().edtb200_transform_voxel_graph(
     labels.ctypes.data, labels.dtype.itemsize, graph.ctypes.data, data.ndim, sx, sy, sz, wx, wy, wz,
     int(bool(black_border)), int(flags), out.ctypes.data, int(device), None))
@@ -307,28 +320,39 @@ def _front_door(data, anisotropy, black_border, voxel_graph, flags, device, fixe
 # public API (signatures follow src/edt.pyx; `device` is keyword-only and additive)
 # ---------------------------------------------------------------------------------------
 
+def _pick(device, devices):
+  """`devices` (a sequence of GPU ordinals: one host volume spread over them) wins over `device`."""
+  if devices is None:
+    return device
+  devs = [int(d) for d in devices]
+  if not devs:
+    raise ValueError("devices must name at least one GPU")
+  return devs if len(devs) > 1 else devs[0]
+
+
 def edtsq(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=None, order=None,
-          *, device=0):
-  """Squared anisotropic multi-label EDT of a 1-D, 2-D or 3-D array (src/edt.pyx:245-310)."""
-  return _front_door(data, anisotropy, black_border, voxel_graph, 0, device)
+          *, device=0, devices=None):
+  """Squared anisotropic multi-label EDT of a 1-D, 2-D or 3-D array (src/edt.pyx:245-310).
+  `devices=[0, 1, ...]` spreads one host volume over several GPUs (see _transform_host)."""
+  return _front_door(data, anisotropy, black_border, voxel_graph, 0, _pick(device, devices))
 
 
 def edt(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=None, order=None,
-        *, device=0):
+        *, device=0, devices=None):
   """Anisotropic multi-label EDT (src/edt.pyx:205-242); the sqrt is fused into the last pass."""
-  return _front_door(data, anisotropy, black_border, voxel_graph, FLAG_SQRT, device)
+  return _front_door(data, anisotropy, black_border, voxel_graph, FLAG_SQRT, _pick(device, devices))
 
 
 def sdf(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=None, order=None,
-        *, device=0):
+        *, device=0, devices=None):
   """Signed distance function, edt(data) - edt(data == 0) (src/edt.pyx:121-158), computed as
   one transform with background as a label and the sign applied in the last store."""
-  return _front_door(data, anisotropy, black_border, voxel_graph, FLAG_SQRT | FLAG_SIGNED, device)
+  return _front_door(data, anisotropy, black_border, voxel_graph, FLAG_SQRT | FLAG_SIGNED, _pick(device, devices))
 
 
-def sdfsq(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=None, *, device=0):
+def sdfsq(data, anisotropy=None, black_border=False, parallel=1, voxel_graph=None, *, device=0, devices=None):
   """Squared signed distance function (src/edt.pyx:161-202)."""
-  return _front_door(data, anisotropy, black_border, voxel_graph, FLAG_SIGNED, device)
+  return _front_door(data, anisotropy, black_border, voxel_graph, FLAG_SIGNED, _pick(device, devices))
 
 
 def edt1dsq(data, anisotropy=1.0, black_border=False, *, device=0):

@@ -881,6 +881,184 @@ int edtb200_slab_face_fixup(const void* labels_dev, int label_bytes, int64_t sx,
   return 0;
 }
 
+// ---- one host volume on several GPUs of this process ---------------------------------------
+// Z slabs for the X and Y passes, Y slabs (whole z lines) for the Z pass: between the two the
+// distances and labels are re-partitioned by peer-to-peer 3-D copies over NVLink, so the result is
+// exact for any input with no halo and no verdict -- for a HOST volume the PCIe copies dominate
+// anyway and every GPU brings its own link.  One host thread per device; the threads meet at two
+// barriers (after the Y passes, after the Z passes), the devices through events.
+namespace {
+
+struct MultiBarrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int waiting = 0, generation = 0, parties = 0, failed = 0;
+  // returns the failure code agreed by all parties (0 = go on)
+  int arrive(int my_rc) {
+    std::unique_lock<std::mutex> l(m);
+    if (my_rc && !failed) failed = my_rc;
+    const int gen = generation;
+    if (++waiting == parties) { waiting = 0; ++generation; cv.notify_all(); }
+    else cv.wait(l, [&] { return generation != gen; });
+    return failed;
+  }
+};
+
+struct MultiPart {
+  int device = 0;
+  int64_t z0 = 0, zc = 0, y0 = 0, yc = 0;
+  void* lz = nullptr; float* fz = nullptr; void* ly = nullptr; float* fy = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t after_y = nullptr, after_z = nullptr;
+  char error[256] = "";
+};
+
+cudaError_t copy_box(void* dst, size_t dst_row_bytes, int64_t dst_rows_per_slice, int dst_dev, int64_t dx_bytes,
+                     int64_t dy, int64_t dz, const void* src, size_t src_row_bytes, int64_t src_rows_per_slice,
+                     int src_dev, int64_t sx_bytes, int64_t sy0, int64_t sz0, size_t width_bytes, int64_t height,
+                     int64_t depth, cudaStream_t stream) {
+  cudaMemcpy3DPeerParms p;
+  memset(&p, 0, sizeof(p));
+  p.srcDevice = src_dev;
+  p.dstDevice = dst_dev;
+  p.srcPtr = make_cudaPitchedPtr(const_cast<void*>(src), src_row_bytes, src_row_bytes, (size_t)src_rows_per_slice);
+  p.dstPtr = make_cudaPitchedPtr(dst, dst_row_bytes, dst_row_bytes, (size_t)dst_rows_per_slice);
+  p.srcPos = make_cudaPos((size_t)sx_bytes, (size_t)sy0, (size_t)sz0);
+  p.dstPos = make_cudaPos((size_t)dx_bytes, (size_t)dy, (size_t)dz);
+  p.extent = make_cudaExtent(width_bytes, (size_t)height, (size_t)depth);
+  return cudaMemcpy3DPeerAsync(&p, stream);
+}
+
+}  // namespace
+
+int edtb200_transform_multi(const void* labels, int label_bytes, int ndim, int64_t sx, int64_t sy, int64_t sz,
+                            float wx, float wy, float wz, int black_border, int flags, float* out,
+                            const int* devices, int ndevices) {
+  using namespace edtb200;
+  if (!devices || ndevices < 1) return fail(EDTB200_EINVAL, "no devices given");
+  if (flags & (EDTB200_LABELS_ON_DEVICE | EDTB200_OUT_ON_DEVICE))
+    return fail(EDTB200_EINVAL, "edtb200_transform_multi splits a HOST volume over the devices");
+  int rc = check_dims(label_bytes, ndim, sx, sy, sz);
+  if (rc) return rc;
+  if (sx * sy * sz == 0) return 0;
+  if (!labels || !out) return fail(EDTB200_EINVAL, "null pointer");
+  for (int i = 0; i < ndevices; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return fail(EDTB200_EINVAL, "device %d listed twice", devices[i]);
+  int G = ndevices;
+  if (ndim < 3) G = 1;
+  if (G > sz) G = (int)sz;
+  if (G > sy) G = (int)sy;
+  if (G <= 1)
+    return edtb200_transform(labels, label_bytes, ndim, sx, sy, sz, wx, wy, wz, black_border, flags, out, devices[0],
+                             nullptr);
+
+  const int border = black_border != 0;
+  const int zero_label = (flags & EDTB200_SIGNED) ? kZeroLabel : 0;
+  const int epilogue = ((flags & EDTB200_SQRT) ? kSqrt : 0) | ((flags & EDTB200_SIGNED) ? kNegate : 0);
+  std::vector<MultiPart> parts(G);
+  for (int d = 0; d < G; ++d) {
+    MultiPart& p = parts[d];
+    p.device = devices[d];
+    p.z0 = sz * d / G; p.zc = sz * (d + 1) / G - p.z0;
+    p.y0 = sy * d / G; p.yc = sy * (d + 1) / G - p.y0;
+  }
+  MultiBarrier barrier;
+  barrier.parties = G;
+  const size_t row_l = (size_t)sx * label_bytes, row_f = (size_t)sx * sizeof(float);
+
+  auto worker = [&](int d) -> int {
+    MultiPart& me = parts[d];
+    DeviceGuard restore_device;
+    DeviceCache* dc = nullptr;
+    int wrc = probe(me.device, &dc);
+    std::unique_lock<std::mutex> host_call;
+    auto note = [&](int code) { snprintf(me.error, sizeof(me.error), "device %d: %.200s", me.device, g_error); return code; };
+    #define MULTI_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess && !wrc) { \
+        wrc = fail(e_ == cudaErrorMemoryAllocation ? EDTB200_ENOMEM : EDTB200_ECUDA, "%s: %s", #expr, \
+                   cudaGetErrorString(e_)); note(wrc); } } while (0)
+    if (!wrc) {
+      host_call = std::unique_lock<std::mutex>(dc->host_call);
+      for (int o = 0; o < G; ++o)                                 // direct NVLink copies where possible
+        if (o != d) { cudaDeviceEnablePeerAccess(parts[o].device, 0); cudaGetLastError(); }
+      if (!dc->stream) MULTI_TRY(cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking));
+      me.stream = dc->stream;
+      MULTI_TRY(cudaEventCreateWithFlags(&me.after_y, cudaEventDisableTiming));
+      MULTI_TRY(cudaEventCreateWithFlags(&me.after_z, cudaEventDisableTiming));
+      const size_t nz_vox = (size_t)sx * sy * me.zc, ny_vox = (size_t)sx * me.yc * sz;
+      MULTI_TRY(scratch_alloc(*dc, &me.lz, nz_vox * label_bytes, me.stream));
+      MULTI_TRY(scratch_alloc(*dc, reinterpret_cast<void**>(&me.fz), nz_vox * sizeof(float), me.stream));
+      MULTI_TRY(scratch_alloc(*dc, &me.ly, ny_vox * label_bytes, me.stream));
+      MULTI_TRY(scratch_alloc(*dc, reinterpret_cast<void**>(&me.fy), ny_vox * sizeof(float), me.stream));
+    } else {
+      note(wrc);
+    }
+    // ---- phase A: my Z slab up, X and Y passes ----
+    if (!wrc) {
+      const char* src = static_cast<const char*>(labels) + (size_t)me.z0 * sy * row_l;
+      wrc = upload(me.lz, src, (size_t)sx * sy * me.zc * label_bytes, me.device, me.stream);
+      if (!wrc) wrc = dispatch_first(label_bytes, me.lz, me.fz, sy * me.zc, sx, wx, border, zero_label, *dc, me.stream);
+      if (!wrc) wrc = dispatch_later(label_bytes, me.lz, me.fz, geom_for_axis(1, sx, sy, me.zc), wy, border, border, 0,
+                                     *dc, me.stream, /*pdl=*/true);
+      if (wrc) note(wrc);
+      MULTI_TRY(cudaEventRecord(me.after_y, me.stream));
+    }
+    int agreed = barrier.arrive(wrc);
+    // ---- phase B: gather my Y slab (whole z lines) from every Z slab, Z pass ----
+    if (!agreed) {
+      for (int o = 0; o < G && !wrc; ++o) {
+        const MultiPart& src = parts[o];
+        MULTI_TRY(cudaStreamWaitEvent(me.stream, src.after_y, 0));
+        MULTI_TRY(copy_box(me.fy, row_f, me.yc, me.device, 0, 0, src.z0, src.fz, row_f, sy, src.device, 0, me.y0, 0,
+                           row_f, me.yc, src.zc, me.stream));
+        MULTI_TRY(copy_box(me.ly, row_l, me.yc, me.device, 0, 0, src.z0, src.lz, row_l, sy, src.device, 0, me.y0, 0,
+                           row_l, me.yc, src.zc, me.stream));
+      }
+      if (!wrc) {
+        wrc = dispatch_later(label_bytes, me.ly, me.fy, geom_for_axis(2, sx, me.yc, sz), wz, border, border, epilogue,
+                             *dc, me.stream, /*pdl=*/false);
+        if (wrc) note(wrc);
+      }
+      MULTI_TRY(cudaEventRecord(me.after_z, me.stream));
+    }
+    agreed = barrier.arrive(wrc);
+    // ---- phase C: my Z slab of the result back from every Y slab, then down to the host ----
+    if (!agreed) {
+      for (int o = 0; o < G && !wrc; ++o) {
+        const MultiPart& src = parts[o];
+        MULTI_TRY(cudaStreamWaitEvent(me.stream, src.after_z, 0));
+        MULTI_TRY(copy_box(me.fz, row_f, sy, me.device, 0, src.y0, 0, src.fy, row_f, src.yc, src.device, 0, 0, me.z0,
+                           row_f, src.yc, me.zc, me.stream));
+      }
+      if (!wrc) {
+        char* dst = reinterpret_cast<char*>(out) + (size_t)me.z0 * sy * row_f;
+        wrc = download(dst, me.fz, (size_t)sx * sy * me.zc * sizeof(float), me.device, me.stream);
+        if (wrc) note(wrc);
+      }
+    }
+    if (me.stream) cudaStreamSynchronize(me.stream);
+    agreed = barrier.arrive(wrc);                                 // nobody frees what a peer may still read
+    void* all[] = {me.lz, me.fz, me.ly, me.fy};
+    for (void* q : all) if (q) cudaFreeAsync(q, me.stream);
+    if (me.after_y) cudaEventDestroy(me.after_y);
+    if (me.after_z) cudaEventDestroy(me.after_z);
+    cudaGetLastError();
+    #undef MULTI_TRY
+    return wrc ? wrc : agreed;
+  };
+
+  std::vector<int> rcs(G, 0);
+  std::vector<std::thread> threads;
+  for (int d = 1; d < G; ++d) threads.emplace_back([&, d] { rcs[d] = worker(d); });
+  rcs[0] = worker(0);
+  for (auto& t : threads) t.join();
+  for (int d = 0; d < G; ++d)
+    if (rcs[d] && parts[d].error[0]) return fail(rcs[d], "%s", parts[d].error);
+  for (int d = 0; d < G; ++d)
+    if (rcs[d]) return fail(rcs[d], "multi-device transform failed on device %d", parts[d].device);
+  return 0;
+}
+
 int64_t edtb200_slab_stage_bytes(int64_t sx, int64_t sy, int label_bytes, int halo) {
   if (sx <= 0 || sy <= 0 || halo < 1 || halo > 254 ||
       !(label_bytes == 1 || label_bytes == 2 || label_bytes == 4 || label_bytes == 8))

@@ -81,6 +81,21 @@ int edtb200_transform(const void *labels, int label_bytes, int ndim,
                       int black_border, int flags,
                       float *out, int device, void *stream);
 
+/* The same transform of ONE host volume spread over several GPUs of this process
+ * (`devices[0..ndevices)`, distinct ordinals): SURVEY.md section 8b's `devices[] / ndevices`.
+ * Every device uploads one Z slab over its own PCIe link and runs the X and Y passes on it; the
+ * distances and labels are then re-partitioned into Y slabs (whole z lines per device) by
+ * peer-to-peer 3-D copies over NVLink, the Z pass runs, the result goes back the same way and
+ * down to `out`.  Exact for any input (no halo, no verdict); `labels` and `out` are HOST pointers
+ * (the *_ON_DEVICE flags are rejected).  Volumes that are not 3-D, or too thin to split, run on
+ * devices[0].  Device memory per GPU: 2 * (label_bytes + 4) * voxels / ndevices.  Calls on
+ * disjoint device sets may run concurrently from different threads. */
+int edtb200_transform_multi(const void *labels, int label_bytes, int ndim,
+                            int64_t sx, int64_t sy, int64_t sz,
+                            float wx, float wy, float wz,
+                            int black_border, int flags,
+                            float *out, const int *devices, int ndevices);
+
 /* Many volumes of one geometry, HOST buffers, pipelined: while volume k is being transformed,
  * volume k+1 is on its way to the device and volume k-1 on its way back (two device slots,
  * separate copy streams, PCIe used in both directions at once).  This is what a caller of the

@@ -312,3 +312,91 @@ def test_slab_split_nccl_two_gpus():
     p.join(timeout=60)
     assert p.exitcode == 0
   assert all(r[1] for r in results), [r for r in results if not r[1]]
+
+
+# ---------------------------------------------------------------------------------------
+# several GPUs behind the boundary: one process, one host volume (edtb200_transform_multi)
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_transform_multi_devices_in_one_process():
+  sys.path.insert(0, ROOT)
+  import edt_b200
+  from oracle import oracle
+  ndev = torch.cuda.device_count()
+  if ndev < 2:
+    pytest.skip("needs two GPUs")
+  rng = np.random.default_rng(5)
+  small = rng.integers(0, 5, (9, 7, 11))
+  lab = np.asfortranarray(np.repeat(np.repeat(np.repeat(small, 9, 0), 13, 1), 10, 2).astype(np.uint16))  # 81x91x110
+  lab[3:70, 5:80, 20:90][rng.uniform(size=(67, 75, 70)) < 0.3] = 0
+  devs = list(range(min(ndev, 4)))
+  for fn, kw in (("edtsq", dict(anisotropy=(1, 1, 1))), ("edt", dict(anisotropy=(2, 1, 3), black_border=True)),
+                 ("sdf", dict(anisotropy=(1.5, 0.5, 2.5)))):
+    want = getattr(oracle, fn)(lab, **kw)
+    got = getattr(edt_b200, fn)(lab, devices=devs, **kw)
+    assert got.flags.f_contiguous and np.array_equal(got, want), fn
+    got_c = getattr(edt_b200, fn)(np.ascontiguousarray(lab), devices=devs, **kw)
+    assert np.array_equal(got_c, want), (fn, "C order")
+  # a volume too thin to split falls back to the first device
+  thin = np.asfortranarray(lab[:, :, :1])
+  assert np.array_equal(edt_b200.edtsq(thin, devices=devs), oracle.edtsq(thin))
+
+
+@pytest.mark.gpu
+def test_two_threads_on_two_gpus_overlap():
+  """Host-buffer transforms on different GPUs from different threads must run concurrently
+  (per-device locks, no library-wide mutex): wall time of two at once < 1.5 x one alone."""
+  sys.path.insert(0, ROOT)
+  import threading
+  import time
+  import edt_b200
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs two GPUs")
+  rng = np.random.default_rng(6)
+  labs = [np.asfortranarray(rng.integers(0, 256, (384, 384, 384), dtype=np.uint32)) for _ in range(2)]
+  for d in range(2):
+    edt_b200.edtsq(labs[d], device=d)                    # warm-up: buffers, streams, copy threads
+  t0 = time.perf_counter()
+  ref0 = edt_b200.edtsq(labs[0], device=0)
+  alone = time.perf_counter() - t0
+  out = [None, None]
+  def work(d):
+    out[d] = edt_b200.edtsq(labs[d], device=d)
+  threads = [threading.Thread(target=work, args=(d,)) for d in range(2)]
+  t0 = time.perf_counter()
+  for t in threads:
+    t.start()
+  for t in threads:
+    t.join()
+  both = time.perf_counter() - t0
+  assert np.array_equal(out[0], ref0)
+  assert both < 1.5 * alone, (alone, both)
+
+
+def _run_slab_check(nproc, extra, timeout):
+  import subprocess
+  cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "slab_check.py")] + extra
+  res = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+  assert res.returncode == 0, res.stdout + res.stderr
+  assert "OK" in res.stdout, res.stdout
+
+
+@pytest.mark.gpu
+def test_slab_check_all_gpus_of_the_box():
+  """The fused slab step (symmetric-memory staging, flag words) on every GPU of the box against the
+  single-GPU transform: edtsq, edt with a border, sdf on 512 x 512 x (64 * N) blocks."""
+  n = torch.cuda.device_count()
+  if n < 2:
+    pytest.skip("needs two GPUs")
+  _run_slab_check(n, ["--depth", "64"], 900)
+
+
+@pytest.mark.gpu
+def test_cfg5_512x512x4096_sdf_eight_gpus():
+  """BASELINE.json configs[4] as written: 512 x 512 x 4096 uint32 multi-label, Z slabs over 8 GPUs,
+  sdf -- every rank's slab bit-equal to the single-GPU sdf of the whole volume."""
+  if torch.cuda.device_count() < 8:
+    pytest.skip("needs eight GPUs")
+  _run_slab_check(8, ["--full"], 1800)
