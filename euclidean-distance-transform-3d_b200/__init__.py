@@ -100,6 +100,10 @@ def _lib():
   lib.edtb200_label_stats.restype = ci
   lib.edtb200_label_extract.argtypes = [vp, ci, vp, i64, i64, i64, ctypes.c_uint64, vp, ci, vp, ci, vp]
   lib.edtb200_label_extract.restype = ci
+  lib.edtb200_host_alloc.argtypes = [ctypes.c_size_t]
+  lib.edtb200_host_alloc.restype = vp
+  lib.edtb200_host_free.argtypes = [vp]
+  lib.edtb200_host_free.restype = None
   lib.edtb200_release.restype = ci
   _LIB = lib
   return lib
@@ -155,6 +159,83 @@ def _x_fastest(shape, anisotropy, f_contiguous):
   return dims, weights
 
 
+# ---------------------------------------------------------------------------------------
+# result arrays backed by recycled page-locked memory
+# ---------------------------------------------------------------------------------------
+# A fresh 512 MiB numpy array costs ~130 000 page faults while the result is copied into it, and
+# pageable memory has to be staged through pinned buffers on the way back from the GPU.  Large
+# results are therefore placed in page-locked blocks (edtb200_host_alloc) that return to a small
+# pool when the array that wraps them is garbage collected: from the second call of a loop on, the
+# download is ONE direct DMA into memory that is already mapped.  The pool holds at most
+# EDTB200_PINNED_POOL_MB (default 2048) of idle blocks and hands out at most twice that in total;
+# beyond it, and for arrays below 4 MiB, plain numpy memory is used.  EDTB200_PINNED_POOL_MB=0
+# turns the pool off.
+
+import threading as _threading
+import weakref as _weakref
+
+_POOL_LOCK = _threading.Lock()
+_POOL_FREE = {}            # nbytes -> [ptr, ...]
+_POOL_IDLE = 0             # bytes sitting in _POOL_FREE
+_POOL_OUT = 0              # bytes currently behind live arrays
+_POOL_MIN = 4 << 20
+
+
+def _pool_cap():
+  try:
+    return int(os.environ.get("EDTB200_PINNED_POOL_MB", "2048")) << 20
+  except ValueError:
+    return 2048 << 20
+
+
+def _pool_release(ptr, nbytes):
+  global _POOL_IDLE, _POOL_OUT
+  with _POOL_LOCK:
+    _POOL_OUT -= nbytes
+    if _POOL_IDLE + nbytes <= _pool_cap():
+      _POOL_FREE.setdefault(nbytes, []).append(ptr)
+      _POOL_IDLE += nbytes
+      return
+  try:
+    _lib().edtb200_host_free(ctypes.c_void_p(ptr))
+  except Exception:        # interpreter shutdown
+    pass
+
+
+def _result_buffer(count):
+  """float32[count] for a result: page-locked and recycled when the pool allows, else np.empty."""
+  global _POOL_IDLE, _POOL_OUT
+  nbytes = int(count) * 4
+  cap = _pool_cap()
+  if nbytes < _POOL_MIN or cap <= 0:
+    return np.empty(count, dtype=np.float32)
+  ptr = None
+  with _POOL_LOCK:
+    free = _POOL_FREE.get(nbytes)
+    if free:
+      ptr = free.pop()
+      _POOL_IDLE -= nbytes
+      _POOL_OUT += nbytes
+    elif _POOL_OUT + nbytes > 2 * cap:
+      return np.empty(count, dtype=np.float32)
+  if ptr is None:
+    lib = _lib()
+    if _POOL_IDLE:                              # make room: drop idle blocks of other sizes
+      with _POOL_LOCK:
+        for size in list(_POOL_FREE):
+          while _POOL_FREE[size] and _POOL_IDLE + nbytes > cap:
+            lib.edtb200_host_free(ctypes.c_void_p(_POOL_FREE[size].pop()))
+            _POOL_IDLE -= size
+    ptr = lib.edtb200_host_alloc(ctypes.c_size_t(nbytes))
+    if not ptr:
+      return np.empty(count, dtype=np.float32)
+    with _POOL_LOCK:
+      _POOL_OUT += nbytes
+  block = (ctypes.c_char * nbytes).from_address(ptr)
+  _weakref.finalize(block, _pool_release, ptr, nbytes)
+  return np.frombuffer(block, dtype=np.float32, count=count)
+
+
 def _transform_host(data, anisotropy, black_border, flags, device):
   nd = data.ndim
   order = "F" if data.flags.f_contiguous else "C"
@@ -164,7 +245,7 @@ def _transform_host(data, anisotropy, black_border, flags, device):
   if labels is None:
     return np.zeros(data.shape, dtype=np.float32, order=order)
   (sx, sy, sz), (wx, wy, wz) = _x_fastest(data.shape, anisotropy, order == "F")
-  out = np.empty(data.size, dtype=np.float32)
+  out = _result_buffer(data.size)
   lib = _lib()
   if isinstance(device, (list, tuple, range)) or (isinstance(device, np.ndarray) and device.ndim == 1):
     # several GPUs of this process share ONE host volume (edtb200_transform_multi): Z slabs for the
@@ -225,7 +306,19 @@ def _device_array(data):
     return data if getattr(data, "is_cuda", False) else None
   if hasattr(data, "__cuda_array_interface__"):
     import torch
-    return torch.as_tensor(data, device="cuda")
+    t = torch.as_tensor(data, device="cuda")
+    # interface v3: "stream" names the stream the producer's work was queued on (1 = legacy
+    # default, 2 = per-thread default, else a cudaStream_t); order torch's current stream after it
+    stream = data.__cuda_array_interface__.get("stream")
+    if stream is not None and stream != 0:
+      cur = torch.cuda.current_stream(t.device)
+      if stream in (1, 2):
+        torch.cuda.synchronize(t.device)
+      elif int(stream) != cur.cuda_stream:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.ExternalStream(int(stream), device=t.device))
+        cur.wait_event(ev)
+    return t
   return None
 
 
@@ -245,8 +338,14 @@ def _front_door_device(t, anisotropy, black_border, voxel_graph, flags, fixed_di
   if t.numel() == 0:
     return torch.zeros(t.shape, dtype=torch.float32, device=t.device)
   if t.dtype in (torch.float32, torch.float64):
-    # labels compare by value (src/edt.pyx:704-722): fold -0.0 onto +0.0, then use the raw bits
-    t = (t + 0).view(torch.int32 if t.dtype == torch.float32 else torch.int64)
+    if voxel_graph is not None:
+      # with a graph the labels only say foreground / background, and for floats the reference
+      # tests `labels[loc] > 0` (src/edt_voxel_graph.hpp:76, 151): negative values and NaN are
+      # background, exactly as on the host path (EDTB200_LABELS_FLOAT)
+      t = (t > 0).to(torch.uint8)
+    else:
+      # labels compare by value (src/edt.pyx:704-722): fold -0.0 onto +0.0, then use the raw bits
+      t = (t + 0).view(torch.int32 if t.dtype == torch.float32 else torch.int64)
   if anisotropy is None:
     anisotropy = (1.0,) * dims
   elif np.ndim(anisotropy) == 0:
@@ -702,5 +801,12 @@ def each(labels, dt, in_place=False, *, device=0):
 
 
 def release():
-  """Free cached device buffers held by the library."""
-  _check(_lib().edtb200_release())
+  """Free cached device buffers held by the library, and the idle page-locked result blocks."""
+  global _POOL_IDLE
+  lib = _lib()
+  with _POOL_LOCK:
+    for size, ptrs in _POOL_FREE.items():
+      while ptrs:
+        lib.edtb200_host_free(ctypes.c_void_p(ptrs.pop()))
+        _POOL_IDLE -= size
+  _check(lib.edtb200_release())

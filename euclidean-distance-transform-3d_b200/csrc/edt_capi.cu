@@ -1088,15 +1088,26 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
   const int epilogue = ((flags & EDTB200_SQRT) ? kSqrt : 0) | ((flags & EDTB200_SIGNED) ? kNegate : 0);
   const edtb200::LineGeom gy = geom_for_axis(1, sx, sy, sz), gz = geom_for_axis(2, sx, sy, sz);
 
+  // EDT_B200_VERBOSE=1: device time of every phase of the step on stderr (synchronises the stream)
+  static const bool verbose = getenv("EDT_B200_VERBOSE") != nullptr && atoi(getenv("EDT_B200_VERBOSE")) != 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  auto stamp = [&](int i) {
+    if (!verbose) return;
+    if (cudaEventCreate(&ev[i]) == cudaSuccess) cudaEventRecord(ev[i], stream);
+    cudaGetLastError();
+  };
+  stamp(0);
   // X and Y passes: slab-local
   nvtx_push("edt.x");
   rc = dispatch_first(label_bytes, labels_dev, f_dev, sy * sz, sx, wx, border, zero_label, *dc, stream);
   nvtx_pop();
   if (rc) return rc;
+  stamp(1);
   nvtx_push("edt.y");
-  rc = dispatch_later(label_bytes, labels_dev, f_dev, gy, wy, border, border, 0, *dc, stream, /*pdl=*/true);
+  rc = dispatch_later(label_bytes, labels_dev, f_dev, gy, wy, border, border, 0, *dc, stream, /*pdl=*/!verbose);
   nvtx_pop();
   if (rc) return rc;
+  stamp(2);
 
   const int64_t plane = sx * sy;
   const SlabStageLayout L = slab_stage_layout(plane, label_bytes, halo);
@@ -1126,6 +1137,7 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
     nvtx_pop();
   }
 
+  stamp(3);
   // Z pass on the slab, interior faces open
   nvtx_push("edt.z");
   rc = dispatch_later(label_bytes, labels_dev, f_dev, gz, wz, border && !has_lo, border && !has_hi, epilogue, *dc,
@@ -1133,6 +1145,7 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
   nvtx_pop();
   if (rc) return rc;
 
+  stamp(4);
   if (has_lo || has_hi) {
     nvtx_push("edt.halo.fixup");
     const int kflags = epilogue | zero_label;
@@ -1154,6 +1167,16 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
 #undef EDT_FIXUP
     CUDA_TRY(cudaGetLastError());
     nvtx_pop();
+  }
+  stamp(5);
+  if (verbose) {
+    float ms[5] = {0, 0, 0, 0, 0};
+    if (ev[5] && cudaEventSynchronize(ev[5]) == cudaSuccess)
+      for (int i = 0; i < 5; ++i) if (ev[i] && ev[i + 1]) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    fprintf(stderr, "[edt_b200] slab step %llu dev %d: x %.3f  y %.3f  stage %.3f  z %.3f  fixup %.3f ms\n", step, device,
+            ms[0], ms[1], ms[2], ms[3], ms[4]);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    cudaGetLastError();
   }
   return 0;
 }
@@ -1231,6 +1254,19 @@ int edtb200_label_extract(const void* labels_dev, int label_bytes, const float* 
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+void* edtb200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void edtb200_host_free(void* p) {
+  if (p) { cudaFreeHost(p); cudaGetLastError(); }
 }
 
 int edtb200_profile_passes(int enable) {

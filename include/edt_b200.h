@@ -232,6 +232,13 @@ int edtb200_label_extract(const void *labels_dev, int label_bytes, const float *
                           int64_t sx, int64_t sy, int64_t sz, unsigned long long key, const int *box,
                           int erase, float *out_dev, int device, void *stream);
 
+/* Page-locked host memory for result arrays (cudaHostAlloc, portable): a transform whose `out` lies
+ * in such a block is copied back by one DMA at PCIe rate, with no staging copy and no page faults.
+ * The Python front door keeps a small pool of these blocks behind the arrays it returns.
+ * edtb200_host_alloc returns NULL when no device / no memory is available. */
+void *edtb200_host_alloc(size_t bytes);
+void edtb200_host_free(void *p);
+
 /* Measurement hooks (used by bench.py): with profiling enabled on the calling thread, every
  * edtb200_transform records CUDA events around its axis passes on the transform's stream into a
  * ring of 256 slots -- nothing synchronises inside a timed loop.  edtb200_pass_ms(k, ms) waits

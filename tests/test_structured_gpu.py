@@ -157,3 +157,17 @@ def test_label_stats_and_each_cuda(edt):
     assert prev is None or img is prev
     assert torch.equal(img, torch.where(lab == key, dt, torch.zeros((), device=dt.device)))
     prev = img
+
+
+def test_device_graph_path_treats_negative_floats_as_background(edt):
+  """With a voxel graph, float labels mean foreground iff value > 0 (src/edt_voxel_graph.hpp:76,
+  151) -- on the device path as on the host path (negative values and NaN are background)."""
+  import torch
+  rng = np.random.default_rng(21)
+  lab = rng.choice(np.array([-2.5, -0.0, 0.0, 1.0, 3.5, np.nan], dtype=np.float32), size=(12, 17, 9))
+  graph = rng.integers(0, 64, lab.shape).astype(np.uint8)
+  host = edt.edtsq(lab, anisotropy=(1, 2, 1), black_border=True, voxel_graph=graph)
+  dev = edt.edtsq(torch.from_numpy(lab).cuda(), anisotropy=(1, 2, 1), black_border=True,
+                  voxel_graph=torch.from_numpy(graph).cuda())
+  assert np.array_equal(dev.cpu().numpy(), host)
+  assert np.all(host[~(lab > 0)] == 0)
