@@ -410,7 +410,7 @@ def ours(args):
   stop.record(stream)
   barrier()
   elapsed_ms = start.elapsed_time(stop)
-  if world == 1:
+  if True:
     # per-pass device times: the same K steps once more with the library recording CUDA events
     # around every pass (on the launch stream, no syncs).  Kept out of the timed region above
     # because an event between two passes keeps the next pass from starting under the previous
@@ -446,11 +446,30 @@ def ours(args):
   if world > 1:
     # the exchange dominates: report the whole step against HBM for orientation only
     alg = (3 * LABEL_BYTES + 20) * nvox
-    roofline = {"bound": "hbm", "kernel": "whole slab step (X, Y, Z passes + %s)" % (
-                    "face fix-up reading the neighbours' faces" if result.get("method") == "halo"
-                    else "Z-slab<->Y-slab transposes"),
-                "achieved": alg / (ms_per_step * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg / (ms_per_step * 1e-3) / 1e9 / peak, "peak_source": peak_src, "traffic": None,
+    # dominant kernel: the Z pass of this rank's slab, timed by the library's per-pass events over the
+    # K steps that followed the timed region (rank 0's slab; every rank runs the same kernels)
+    zms = None
+    try:
+      buf3 = (ctypes.c_float * 3)()
+      zs = []
+      for back in range(min(args.steps, 250)):
+        check(lib.edtb200_pass_ms(back, ctypes.cast(buf3, ctypes.c_void_p)))
+        zs.append(float(buf3[2]))
+      zms = statistics.mean(zs) if zs else None
+    except Exception:
+      zms = None
+    zalg = (LABEL_BYTES + 8) * nvox
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "later_axis_tile_kernel<4,32,false,true,false> (Z pass of one slab)",
+                "achieved": (zalg / (zms * 1e-3) / 1e9) if zms else None, "peak": peak, "unit": "GB/s",
+                "frac": (zalg / (zms * 1e-3) / 1e9 / peak) if zms else None, "peak_source": peak_src,
+                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                "algorithmic_bytes_per_launch": zalg, "ms": zms,
+                "whole_step": {"what": "X, Y, Z passes + %s, per rank" % (
+                                   "face staging and fix-up reading the neighbours' faces over NVLink"
+                                   if result.get("method") == "halo" else "Z-slab<->Y-slab transposes"),
+                               "algorithmic_bytes": alg, "GBps": alg / (ms_per_step * 1e-3) / 1e9,
+                               "frac": alg / (ms_per_step * 1e-3) / 1e9 / peak},
                 "nvlink_bytes_per_gpu_per_step": (2 * 512 * 512 * (2 * 4 + LABEL_BYTES + 1)
                                                   if result.get("method") == "halo"
                                                   else int(nvox * (LABEL_BYTES + 8) * (world - 1) / world))}

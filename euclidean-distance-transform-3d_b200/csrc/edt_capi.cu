@@ -341,6 +341,21 @@ int probe(int device, DeviceCache** out) {
       dc.pool = nullptr;                 // fall back to the default pool, settings untouched
     }
     cudaGetLastError();
+    // run statistic of the first-axis pass: two device counters and two mapped host words
+    void* stat = nullptr;
+    void* host = nullptr;
+    if (cudaMalloc(&stat, 64) == cudaSuccess && cudaMemset(stat, 0, 64) == cudaSuccess &&
+        cudaHostAlloc(&host, 64, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+      memset(host, 0, 64);
+      void* host_dev = nullptr;
+      if (cudaHostGetDevicePointer(&host_dev, host, 0) == cudaSuccess) {
+        dc.stat_counter = static_cast<unsigned long long*>(stat);
+        dc.stat_ticket = reinterpret_cast<unsigned int*>(static_cast<char*>(stat) + 16);
+        dc.stat_publish_host = static_cast<volatile unsigned long long*>(host);
+        dc.stat_publish_dev = static_cast<unsigned long long*>(host_dev);
+      }
+    }
+    cudaGetLastError();
     dc.probed = true;
   }
   *out = &dc;
@@ -1097,12 +1112,14 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
     cudaGetLastError();
   };
   stamp(0);
+  mark_pass(0, stream);              // per-pass events for bench.py (edtb200_profile_passes), as in run_passes
   // X and Y passes: slab-local
   nvtx_push("edt.x");
   rc = dispatch_first(label_bytes, labels_dev, f_dev, sy * sz, sx, wx, border, zero_label, *dc, stream);
   nvtx_pop();
   if (rc) return rc;
   stamp(1);
+  mark_pass(1, stream);
   nvtx_push("edt.y");
   rc = dispatch_later(label_bytes, labels_dev, f_dev, gy, wy, border, border, 0, *dc, stream, /*pdl=*/!verbose);
   nvtx_pop();
@@ -1138,6 +1155,7 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
   }
 
   stamp(3);
+  mark_pass(2, stream);              // "second pass" = Y plus the face staging kernel
   // Z pass on the slab, interior faces open
   nvtx_push("edt.z");
   rc = dispatch_later(label_bytes, labels_dev, f_dev, gz, wz, border && !has_lo, border && !has_hi, epilogue, *dc,
@@ -1146,6 +1164,7 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
   if (rc) return rc;
 
   stamp(4);
+  mark_pass(3, stream);
   if (has_lo || has_hi) {
     nvtx_push("edt.halo.fixup");
     const int kflags = epilogue | zero_label;

@@ -67,6 +67,11 @@ struct DeviceCache {
   Table tables[kTables];
   uint64_t table_clock = 0;
   cudaMemPool_t pool = nullptr;        // private pool of the stream-ordered scratch allocations
+  // run statistic of the first-axis pass (see RunStat): device counters + a mapped host word pair
+  unsigned long long* stat_counter = nullptr;
+  unsigned int* stat_ticket = nullptr;
+  volatile unsigned long long* stat_publish_host = nullptr;
+  unsigned long long* stat_publish_dev = nullptr;
   int sm_count = 0;
   int max_smem_optin = 0;
   bool probed = false;

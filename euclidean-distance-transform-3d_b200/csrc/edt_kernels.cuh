@@ -54,6 +54,34 @@ __device__ __forceinline__ float finish_value(float v, bool background, int flag
   return v;
 }
 
+// Statistic of the first-axis pass for the host's NEXT launch decisions: how many runs of equal
+// labels the volume has along x.  Every warp adds its count to `counter`; the last CTA of the grid
+// moves the total (and the voxel count) to `publish` -- page-locked host memory mapped into the
+// device -- and resets the counters, so nothing has to be zeroed between transforms and the host
+// never synchronises to read it (it looks at the value the previous transform left there).
+struct RunStat {
+  unsigned long long* counter;     // device
+  unsigned int* ticket;            // device
+  unsigned long long* publish;     // mapped host memory: [0] run starts, [1] voxels
+  unsigned long long voxels;
+};
+
+__device__ __forceinline__ void publish_run_stat(const RunStat st, unsigned int warp_total, int lane) {
+  if (!st.counter) return;
+  if (lane == 0 && warp_total) atomicAdd(st.counter, (unsigned long long)warp_total);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(st.ticket, 1u) == gridDim.x - 1u) {
+      const unsigned long long total = atomicExch(st.counter, 0ull);
+      *st.ticket = 0u;
+      st.publish[0] = total;
+      st.publish[1] = st.voxels;
+      __threadfence_system();
+    }
+  }
+}
+
 // T[k] for k = 0..count-1 (see header).  One thread: the adds are sequential by definition
 // (src/edt.hpp:92-118 accumulates d[i] = d[i-1] + w in float32).
 static __global__ void step_table_kernel(float w, int count, float* __restrict__ table) {
@@ -80,7 +108,7 @@ template <int Bytes>
 __global__ void __launch_bounds__(256)
 first_axis_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
                   float* __restrict__ out, int64_t nlines, int sx,
-                  const float* __restrict__ table, int border, int flags) {
+                  const float* __restrict__ table, int border, int flags, RunStat stat) {
   using LT = typename LabelOf<Bytes>::type;
   using WT = typename LabelOf<Bytes>::wide;
   extern __shared__ uint32_t smem_u32[];
@@ -97,6 +125,7 @@ first_axis_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
   int* below = reinterpret_cast<int*>(bkg + nwords);   // nearest set bit in words < c
   int* above = below + nwords;                          // nearest set bit in words > c
 
+  unsigned int nstarts = 0;                            // label changes seen by this warp (lane 0 counts)
   for (int64_t line = (int64_t)blockIdx.x * warps + warp; line < nlines;
        line += (int64_t)gridDim.x * warps) {
     const LT* __restrict__ src = labels + line * sx;
@@ -125,7 +154,7 @@ first_axis_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
           else edge = (p == sx) && (border != 0);
           const uint32_t wb = __ballot_sync(full, edge);
           const uint32_t wz = __ballot_sync(full, (p < sx) && (v[u] == 0));
-          if (lane == 0) { bnd[c] = wb; bkg[c] = wz; }
+          if (lane == 0) { bnd[c] = wb; bkg[c] = wz; nstarts += __popc(wb); }
         }
       }
     }
@@ -189,6 +218,7 @@ first_axis_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
     }
     __syncwarp();
   }
+  publish_run_stat(stat, nstarts, lane);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -233,7 +263,7 @@ template <int Bytes, int K, bool Plain>
 __global__ void __launch_bounds__(256)
 first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
                       float* __restrict__ out, int64_t nlines, int sx,
-                      const float* __restrict__ table, int border, int flags) {
+                      const float* __restrict__ table, int border, int flags, RunStat stat) {
   using LT = typename LabelOf<Bytes>::type;
   using WT = typename LabelOf<Bytes>::wide;
   extern __shared__ float table_s[];                 // T[0..sx], then +inf at sx + 1
@@ -249,6 +279,7 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
   const unsigned lt_mask = (1u << lane) - 1u;
   const unsigned gt_mask = (lane == 31) ? 0u : (0xfffffffeu << lane);
   const bool keep_background = Plain ? false : (flags & kZeroLabel) != 0;
+  unsigned int nstarts = 0;                          // label changes along x seen by this lane
 
   for (int64_t line = (int64_t)blockIdx.x * warps + warp; line < nlines;
        line += (int64_t)gridDim.x * warps) {
@@ -288,6 +319,7 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
       edges |= m << (4 * b);
       zeros |= z << (4 * b);
     }
+    nstarts += __popc(edges);
 
     // ---- nearest boundary strictly below / above the lane's 4 voxels, per block ----
     // The ballots give the boundary-owning lanes; one shuffle fetches that lane's masks.
@@ -352,6 +384,11 @@ first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
       *reinterpret_cast<float4*>(dst + q0) = make_float4(r[0], r[1], r[2], r[3]);
     }
   }
+  if (stat.counter) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) nstarts += __shfl_xor_sync(full, nstarts, s);
+  }
+  publish_run_stat(stat, nstarts, lane);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -702,8 +739,12 @@ __device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, u
   }
 }
 
-template <int Bytes, int TX, bool Epilogue, bool UseTMA, bool Wide>
-__global__ void __launch_bounds__(Wide ? 1024 : 512, Wide ? 1 : 3)
+// MinCtas: CTAs of 512 threads per SM the kernel is compiled for.  3 (40 registers, a few spills)
+// is what the envelope stages want -- they are latency-bound and the third CTA's warps hide it;
+// 2 (60 registers, no spills) is faster when nearly every run is one row long (label noise), where
+// only the streaming path runs.  The host picks per launch (edt_passes.cuh).
+template <int Bytes, int TX, bool Epilogue, bool UseTMA, bool Wide, int MinCtas>
+__global__ void __launch_bounds__(Wide ? 1024 : 512, Wide ? 1 : MinCtas)
 later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
                        const typename LabelOf<Bytes>::type* __restrict__ labels,
                        float* __restrict__ f, LineGeom g, TileBoxes tb, float w2,
