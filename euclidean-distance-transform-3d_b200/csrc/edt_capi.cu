@@ -210,7 +210,7 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes, int dir, int devi
     // measured on the B200 host (2 x 64 threads), 512 MiB each way: 8 threads 40 ms, 16 threads
     // 31 ms, 32 threads 38 ms per numpy-to-numpy call; populating the fresh output array's pages
     // from helper threads during the upload was tried and only made it slower (44-68 ms)
-    int n = hw >= 32 ? 16 : (hw >= 16 ? 8 : (hw >= 4 ? 4 : 1));
+    int n = hw >= 48 ? 24 : (hw >= 32 ? 16 : (hw >= 16 ? 8 : (hw >= 4 ? 4 : 1)));     // r02 sweep: 24 threads 22-25 ms, 16: 25-27, 32: 27
     if (const char* e = getenv("EDTB200_COPY_THREADS")) n = std::max(1, std::min(64, atoi(e)));
     g_pool = new CopyPool(n);
   }
@@ -223,7 +223,12 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes, int dir, int devi
   });
 }
 
-constexpr size_t kStageBytes = size_t(32) << 20;
+// size of one staging buffer (EDTB200_STAGE_MB, 4..256, default 32) and how many rotate
+const size_t kStageBytes = [] {
+  size_t mb = 32;
+  if (const char* e = getenv("EDTB200_STAGE_MB")) mb = (size_t)std::max(4, std::min(256, atoi(e)));
+  return mb << 20;
+}();
 constexpr int kStages = 3;
 struct StageBuffers {
   void* buf[kStages] = {nullptr, nullptr, nullptr};
@@ -384,14 +389,31 @@ int dispatch_first(int label_bytes, const void* labels, float* f, int64_t nlines
   }
 }
 
+// fmax: an upper bound of the finite samples in f when they are known to be integer-valued (the
+// product of earlier passes with integer weights^2), or -1: enables the integer hull tests.
 int dispatch_later(int label_bytes, const void* labels, float* f, const edtb200::LineGeom& g, float w,
-                   int lo, int hi, int flags, DeviceCache& dc, cudaStream_t s, bool pdl = false) {
+                   int lo, int hi, int flags, DeviceCache& dc, cudaStream_t s, bool pdl = false, double fmax = -1.0) {
   switch (label_bytes) {
-    case 1: return launch_later<1>(labels, f, g, w, lo, hi, flags, dc, s, pdl);
-    case 2: return launch_later<2>(labels, f, g, w, lo, hi, flags, dc, s, pdl);
-    case 4: return launch_later<4>(labels, f, g, w, lo, hi, flags, dc, s, pdl);
-    default: return launch_later<8>(labels, f, g, w, lo, hi, flags, dc, s, pdl);
+    case 1: return launch_later<1>(labels, f, g, w, lo, hi, flags, dc, s, pdl, fmax);
+    case 2: return launch_later<2>(labels, f, g, w, lo, hi, flags, dc, s, pdl, fmax);
+    case 4: return launch_later<4>(labels, f, g, w, lo, hi, flags, dc, s, pdl, fmax);
+    default: return launch_later<8>(labels, f, g, w, lo, hi, flags, dc, s, pdl, fmax);
   }
+}
+
+// Largest finite value the passes along axes of lengths n[0..k) with weights w[0..k) can have
+// produced, if all their squared weights (the float products the kernels use) are integers and
+// the distances stay exact in float32; else -1.  (An X-pass value is fl32(a_k^2) with a_k = k*w
+// exact below 2^24; a later pass adds w2 * d^2 to an earlier value.)
+double integer_bound(const float* w, const int64_t* n, int k) {
+  double bound = 0.0;
+  for (int i = 0; i < k; ++i) {
+    const float w2 = w[i] * w[i];
+    if (!(w2 == floorf(w2)) || w2 < 1.0f) return -1.0;
+    if (i == 0 && !((double)w[0] == floor((double)w[0]) && (double)w[0] * (double)n[0] < 16777216.0)) return -1.0;
+    bound += (double)w2 * (double)n[i] * (double)n[i];
+  }
+  return bound < 2147483000.0 ? bound : -1.0;
 }
 
 edtb200::LineGeom geom_for_axis(int axis, int64_t sx, int64_t sy, int64_t sz) {
@@ -487,14 +509,17 @@ int run_passes(const void* labels, int label_bytes, int ndim, int64_t sx, int64_
   mark_pass(1, stream);
   if (!rc && ndim >= 2) {
     nvtx_push("edt.y");
+    const float ws[1] = {wx}; const int64_t ns[1] = {sx};
     rc = dispatch_later(label_bytes, labels, f, gy, wy, border, border, ndim == 2 ? epilogue : 0, dc, stream,
-                        /*pdl=*/true);
+                        /*pdl=*/true, integer_bound(ws, ns, 1));
     nvtx_pop();
     mark_pass(2, stream);
   }
   if (!rc && ndim >= 3) {
     nvtx_push("edt.z");
-    rc = dispatch_later(label_bytes, labels, f, gz, wz, border, border, epilogue, dc, stream, /*pdl=*/true);
+    const float ws[2] = {wx, wy}; const int64_t ns[2] = {sx, sy};
+    rc = dispatch_later(label_bytes, labels, f, gz, wz, border, border, epilogue, dc, stream, /*pdl=*/true,
+                        integer_bound(ws, ns, 2));
     nvtx_pop();
     mark_pass(3, stream);
   }
@@ -1013,8 +1038,10 @@ int edtb200_transform_multi(const void* labels, int label_bytes, int ndim, int64
       const char* src = static_cast<const char*>(labels) + (size_t)me.z0 * sy * row_l;
       wrc = upload(me.lz, src, (size_t)sx * sy * me.zc * label_bytes, me.device, me.stream);
       if (!wrc) wrc = dispatch_first(label_bytes, me.lz, me.fz, sy * me.zc, sx, wx, border, zero_label, *dc, me.stream);
+      const float ws[2] = {wx, wy};
+      const int64_t ns[2] = {sx, sy};
       if (!wrc) wrc = dispatch_later(label_bytes, me.lz, me.fz, geom_for_axis(1, sx, sy, me.zc), wy, border, border, 0,
-                                     *dc, me.stream, /*pdl=*/true);
+                                     *dc, me.stream, /*pdl=*/true, integer_bound(ws, ns, 1));
       if (wrc) note(wrc);
       MULTI_TRY(cudaEventRecord(me.after_y, me.stream));
     }
@@ -1030,8 +1057,10 @@ int edtb200_transform_multi(const void* labels, int label_bytes, int ndim, int64
                            row_l, me.yc, src.zc, me.stream));
       }
       if (!wrc) {
+        const float ws[2] = {wx, wy};
+        const int64_t ns[2] = {sx, sy};
         wrc = dispatch_later(label_bytes, me.ly, me.fy, geom_for_axis(2, sx, me.yc, sz), wz, border, border, epilogue,
-                             *dc, me.stream, /*pdl=*/false);
+                             *dc, me.stream, /*pdl=*/false, integer_bound(ws, ns, 2));
         if (wrc) note(wrc);
       }
       MULTI_TRY(cudaEventRecord(me.after_z, me.stream));
@@ -1121,7 +1150,10 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
   stamp(1);
   mark_pass(1, stream);
   nvtx_push("edt.y");
-  rc = dispatch_later(label_bytes, labels_dev, f_dev, gy, wy, border, border, 0, *dc, stream, /*pdl=*/!verbose);
+  const float ws[2] = {wx, wy};
+  const int64_t ns[2] = {sx, sy};
+  rc = dispatch_later(label_bytes, labels_dev, f_dev, gy, wy, border, border, 0, *dc, stream, /*pdl=*/!verbose,
+                      integer_bound(ws, ns, 1));
   nvtx_pop();
   if (rc) return rc;
   stamp(2);
@@ -1159,7 +1191,7 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
   // Z pass on the slab, interior faces open
   nvtx_push("edt.z");
   rc = dispatch_later(label_bytes, labels_dev, f_dev, gz, wz, border && !has_lo, border && !has_hi, epilogue, *dc,
-                      stream, /*pdl=*/false);
+                      stream, /*pdl=*/false, integer_bound(ws, ns, 2));
   nvtx_pop();
   if (rc) return rc;
 

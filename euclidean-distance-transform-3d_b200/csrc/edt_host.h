@@ -92,7 +92,7 @@ int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float
                  DeviceCache& dc, cudaStream_t stream);
 template <int Bytes>
 int launch_later(const void* labels, float* f, const LineGeom& g0, float w, int border_lo, int border_hi,
-                 int flags, DeviceCache& dc, cudaStream_t stream, bool pdl);
+                 int flags, DeviceCache& dc, cudaStream_t stream, bool pdl, double fmax);
 
 // Shared memory of one tile of `tx` lines (see later_axis_tile_kernel); tile_path_ok tells whether
 // launch_later takes the shared-memory tile kernel for this geometry.

@@ -521,9 +521,9 @@ struct TileLine {
   uint32_t hull;   // &hullw[0][x]
   __device__ __forceinline__ float fval(int pos) const { return lds_f32(f + (uint32_t)pos * ROW); }
   __device__ __forceinline__ uint32_t hword(int wi) const { return lds_u32_volatile(hull + (uint32_t)wi * ROW); }
-  __device__ __forceinline__ void drop(int pos) const {
-    const uint32_t at = hull + (uint32_t)(pos >> 5) * ROW;
-    sts_u32(at, lds_u32_volatile(at) & ~(1u << (pos & 31)));
+  __device__ __forceinline__ void drop(int pos) const {      // atomic: two runs may share a word
+    asm volatile("red.shared.and.b32 [%0], %1;" ::"r"(hull + (uint32_t)(pos >> 5) * ROW), "r"(~(1u << (pos & 31)))
+                 : "memory");
   }
 };
 
@@ -535,6 +535,19 @@ __device__ __forceinline__ bool vertex_hidden(int l, float fl, int m, float fm, 
   const double nml = ((double)fm - (double)fl) + w2 * (dml * (double)(m + l));
   const double nrm = ((double)fr - (double)fm) + w2 * (drm * (double)(r + m));
   return nrm * dml <= nml * drm;
+}
+
+// The same test in exact integer arithmetic, for passes whose samples are integer-valued and small
+// enough (decided by the host, see launch_later): with g(v) = f[v] + w2 * v^2 < 2^31 the numerators
+// are g differences, the denominators position differences, and each side of the cross
+// multiplication is one 32 x 32 -> 64-bit product.  No FP64 operations, no conversions to double,
+// and a third of the registers -- the envelope stages run at 40 registers per thread.
+__device__ __forceinline__ int g_value(float f, int pos, int w2i) {
+  return __float2int_rn(f) + w2i * (pos * pos);
+}
+__device__ __forceinline__ bool vertex_hidden_int(int l, float fl, int m, float fm, int r, float fr, int w2i) {
+  const int gl = g_value(fl, l, w2i), gm = g_value(fm, m, w2i), gr = g_value(fr, r, w2i);
+  return (long long)(gr - gm) * (long long)(m - l) <= (long long)(gm - gl) * (long long)(r - m);
 }
 
 // Largest vertex v with a <= v < pos, or -1.
@@ -641,6 +654,39 @@ __device__ __forceinline__ uint32_t build_hull_rows(const TileLine<TX> ln, int i
   return hb;
 }
 
+// build_hull_rows in exact integer arithmetic (see vertex_hidden_int): top vertex q with g(q),
+// the vertex below it p with g(p); q is hidden by the newcomer r when
+// (g(r) - g(q)) * (q - p) <= (g(q) - g(p)) * (r - q).
+template <int TX>
+__device__ __forceinline__ uint32_t build_hull_rows_int(const TileLine<TX> ln, int i0, uint32_t todo, uint32_t starts,
+                                                        int w2i, uint32_t hb) {
+  const float inf = __int_as_float(0x7f800000);
+  int cnt = 0, q = 0, p = 0, gq = 0, gp = 0;                  // rows relative to i0
+  uint32_t segmask = 0xffffffffu;
+  for (uint32_t rest = todo; rest; rest &= rest - 1u) {
+    const int r = __ffs(rest) - 1;
+    if ((starts >> r) & 1u) { cnt = 0; segmask = 0xffffffffu << r; }
+    const float fr = ln.fval(i0 + r);
+    if (!(fr < inf)) continue;                                // +inf: not a site
+    const int gr = g_value(fr, i0 + r, w2i);
+    while (cnt >= 2 && (long long)(gr - gq) * (long long)(q - p) <= (long long)(gq - gp) * (long long)(r - q)) {
+      hb &= ~(1u << q);                                       // q is hidden
+      --cnt;
+      q = p; gq = gp;
+      if (cnt >= 2) {
+        const uint32_t m = hb & segmask & ((1u << q) - 1u);
+        p = 31 - __clz(m);
+        gp = g_value(ln.fval(i0 + p), i0 + p, w2i);
+      }
+    }
+    hb |= 1u << r;
+    ++cnt;
+    p = q; gp = gq;
+    q = r; gq = gr;
+  }
+  return hb;
+}
+
 // Outputs of the rows in `todo` (bit = row - i0): rows of runs that lie INSIDE the chunk (first
 // row at a bit of `starts`, last row at a bit of `ends`).  One loop over the marked rows for every
 // lane; a run's state is set up at its first row.  A run whose rows are not marked in `noncst` is
@@ -698,12 +744,30 @@ __device__ __forceinline__ void read_out_rows_local(const TileLine<TX> ln, int i
 }
 
 // State of the walk along the final hull of a run [a, b) that crosses chunk boundaries, for the
-// rows of one chunk; see read_out_rows_crossing.
+// rows of one chunk: current vertex v, next vertex v1, and an iterator over the vertices above v1
+// (`rem` = the not yet visited vertex bits of hull word `wi`, clipped to the run in its last word).
 struct HullWalk {
-  int a, b, v, v1;
+  int a, b, v, v1, wi;
+  uint32_t rem;
   float fv, fv1, dv, dv1;
   bool lo_b, hi_b, cst, bg;
 };
+
+// v1 <- the next vertex of the run above the current v1 (or -1), and its sample.
+template <int TX>
+__device__ __forceinline__ void walk_advance(HullWalk& w, const TileLine<TX> ln, int row) {
+  const int wb = (w.b - 1) >> 5;
+  while (!w.rem) {
+    if (w.wi >= wb) { w.v1 = -1; return; }
+    ++w.wi;
+    w.rem = ln.hword(w.wi);
+    if (w.wi == wb) w.rem &= 0xffffffffu >> (31 - ((w.b - 1) & 31));
+  }
+  w.v1 = (w.wi << 5) + __ffs(w.rem) - 1;
+  w.rem &= w.rem - 1u;
+  w.fv1 = ln.fval(w.v1);
+  w.dv1 = (float)(row - w.v1);
+}
 
 // Sets the walk up for row `lo` of the run [a, b): the vertex that dominates row lo is found by
 // starting at the nearest vertex at or below lo (else the first one above) and descending along
@@ -718,6 +782,7 @@ __device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, u
   w.bg = background;
   w.cst = all_const || run_is_constant<TX>(ln, cflagcol, a, b);
   w.v = w.v1 = -1; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
+  w.wi = 0; w.rem = 0u;
   if (w.cst) return;
   int v = prev_vertex<TX>(ln, lo + 1, a);
   if (v < 0) v = next_vertex<TX>(ln, lo, b);
@@ -734,8 +799,12 @@ __device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, u
       best = cand; v = u; fv = fu; dv = du;
     }
     w.v = v; w.fv = fv; w.dv = dv;
-    w.v1 = next_vertex<TX>(ln, v, b);
-    if (w.v1 >= 0) { w.fv1 = ln.fval(w.v1); w.dv1 = (float)(lo - w.v1); }
+    // iterator over the vertices above v
+    const int wb = (b - 1) >> 5;
+    w.wi = v >> 5;
+    w.rem = ((v & 31) == 31) ? 0u : (ln.hword(w.wi) & (0xfffffffeu << (v & 31)));
+    if (w.wi == wb) w.rem &= 0xffffffffu >> (31 - ((b - 1) & 31));
+    walk_advance<TX>(w, ln, lo);
   }
 }
 
@@ -743,12 +812,14 @@ __device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, u
 // is what the envelope stages want -- they are latency-bound and the third CTA's warps hide it;
 // 2 (60 registers, no spills) is faster when nearly every run is one row long (label noise), where
 // only the streaming path runs.  The host picks per launch (edt_passes.cuh).
-template <int Bytes, int TX, bool Epilogue, bool UseTMA, bool Wide, int MinCtas>
+// IntHull: hull tests in exact integer arithmetic (the host guarantees integer-valued samples with
+// f + w2 * n^2 < 2^31 and passes w2 as an integer in `w2i`); otherwise in double.
+template <int Bytes, int TX, bool Epilogue, bool UseTMA, bool Wide, int MinCtas, bool IntHull>
 __global__ void __launch_bounds__(Wide ? 1024 : 512, Wide ? 1 : MinCtas)
 later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
                        const typename LabelOf<Bytes>::type* __restrict__ labels,
                        float* __restrict__ f, LineGeom g, TileBoxes tb, float w2,
-                       int border_lo, int border_hi, int flags) {
+                       int border_lo, int border_hi, int flags, int w2i) {
   using LT = typename LabelOf<Bytes>::type;
   extern __shared__ __align__(128) unsigned char smem_tile[];
   constexpr int SUBS = 32 / TX;                       // chunks handled side by side by one warp
@@ -940,7 +1011,8 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           if ((noncst & cross_mask) || (entering && ln.fval(i0) != ln.fval(i0 - 1))) any_cross |= 2;
         }
         // (1c) hulls of the non-constant segments
-        if (noncst) hb = build_hull_rows<TX>(ln, i0, noncst, starts, w2d, hb);
+        if (noncst) hb = IntHull ? build_hull_rows_int<TX>(ln, i0, noncst, starts, w2i, hb)
+                                 : build_hull_rows<TX>(ln, i0, noncst, starts, w2d, hb);
         // (1d) the local runs are finished here
         const uint32_t local = multi & ~cross_mask;
         if (local)
@@ -956,72 +1028,81 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   const bool all_const = !__syncthreads_or(any_cross & 2);
 
   // ============ stage 2: stitch the hulls of runs that cross chunk boundaries ============
-  // Divide and conquer over the chunks: at level l the groups of 2^(l-1) chunks left and right
-  // of every boundary that is a multiple of 2^(l-1) but not of 2^l are merged, all boundaries
-  // of a level (and all lines) in parallel.  Left of a boundary stands the finished hull of the
-  // run's rows in the left group (A), right of it the finished hull of its rows in the right
-  // group (B).  All of A lies left of all of B, so the hull of the union is a prefix of A plus
-  // a suffix of B: drop A's top while it is hidden by (the vertex below it, B's first), drop
-  // B's first while it is hidden by (A's top, B's second), until neither applies.
-  int levels = 0;
-  while ((1 << levels) < nchunks) ++levels;
-  if (all_const) levels = 0;
-  for (int lev = 1; lev <= levels; ++lev) {
-    const int half = 1 << (lev - 1);
-    if (live) {
-      for (int c = chunk0; c < nchunks; c += chunk_step) {
-        if ((c & ((half << 1) - 1)) != half) continue;     // c = first chunk of a right group
-        const int i0 = c << 5;
-        const uint32_t wc = lds_u32(startcol + (uint32_t)c * ROW);
-        if (wc & 1u) continue;                             // a run starts exactly here: nothing crosses
-        int a = 0;                                         // start of the run that crosses
-        for (int cc = c - 1; cc >= 0; --cc) {
-          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
-          if (w) { a = (cc << 5) + 31 - __clz(w); break; }
-        }
-        int b = n;                                         // its end (exclusive)
-        for (int cc = c; cc < nchunks; ++cc) {
-          const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
-          if (w) { b = min(n, (cc << 5) + __ffs(w) - 1); break; }
-        }
-        if (lev == 1) {
-          // (first level only: later levels see hulls that earlier merges may have thinned out)
-          // equal-height rows on both sides of the boundary cannot hide one another: when the two
-          // adjacent chunk segments are constant and equal there is nothing to drop here
-          const uint32_t fl_hi = lds_u8_volatile(cflagcol + (uint32_t)c * TX);
-          const uint32_t fl_lo = lds_u8_volatile(cflagcol + (uint32_t)(c - 1) * TX);
-          const bool lo_const = (a >= ((c - 1) << 5)) ? (fl_lo & 2u) != 0 : (fl_lo & 1u) != 0;
-          if ((fl_hi & 1u) && lo_const && ln.fval(i0) == ln.fval(i0 - 1)) continue;
-        }
-        const int alo = max(a, (c - half) << 5);           // the run's rows inside the two groups
-        const int bhi = min(b, min(n, (c + half) << 5));
-        int av = prev_vertex<TX>(ln, i0, alo);
-        int bv = next_vertex<TX>(ln, i0 - 1, bhi);
-        if (av < 0 || bv < 0) continue;
-        int ap = prev_vertex<TX>(ln, av, alo);
-        int bn = next_vertex<TX>(ln, bv, bhi);
-        float fa = ln.fval(av), fb = ln.fval(bv);
-        float fap = ap >= 0 ? ln.fval(ap) : 0.0f, fbn = bn >= 0 ? ln.fval(bn) : 0.0f;
-        for (;;) {
-          if (ap >= 0 && vertex_hidden(ap, fap, av, fa, bv, fb, w2d)) {         // A's top is hidden
-            ln.drop(av);
-            av = ap; fa = fap;
-            ap = prev_vertex<TX>(ln, av, alo);
-            if (ap >= 0) fap = ln.fval(ap);
-            continue;
+  // Divide and conquer over the chunk segments of every run: the boundaries of a run are numbered
+  // j = 1, 2, ... from the chunk the run starts in; in the round with group size `half` every
+  // boundary with j = half (mod 2 half) merges the `half` segments left of it with the (up to)
+  // `half` segments right of it, all runs, boundaries and lines in parallel.  Left of a boundary
+  // stands the finished hull of the run's rows in the left group (A), right of it the finished hull
+  // of its rows in the right group (B).  All of A lies left of all of B, so the hull of the union
+  // is a prefix of A plus a suffix of B: drop A's top while it is hidden by (the vertex below it,
+  // B's first), drop B's first while it is hidden by (A's top, B's second), until neither applies.
+  // Numbering the boundaries per run (not per line) keeps the number of rounds -- each ends in a
+  // CTA-wide barrier -- at log2 of the longest run's chunk count instead of log2 of the line's:
+  // two rounds for runs of up to 128 rows.  Boundaries of different runs may meet in one hull word,
+  // so bits are dropped with an atomic AND.
+  if (!all_const) {
+    for (int half = 1; half < nchunks; half <<= 1) {
+      int more = 0;
+      if (live) {
+        for (int c = chunk0; c < nchunks; c += chunk_step) {
+          if (c == 0) continue;                              // no boundary below the first chunk
+          const int i0 = c << 5;
+          const uint32_t wc = lds_u32(startcol + (uint32_t)c * ROW);
+          if (wc & 1u) continue;                             // a run starts exactly here: nothing crosses
+          int a = 0;                                         // start of the run that crosses
+          for (int cc = c - 1; cc >= 0; --cc) {
+            const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+            if (w) { a = (cc << 5) + 31 - __clz(w); break; }
           }
-          if (bn >= 0 && vertex_hidden(av, fa, bv, fb, bn, fbn, w2d)) {         // B's first is hidden
-            ln.drop(bv);
-            bv = bn; fb = fbn;
-            bn = next_vertex<TX>(ln, bv, bhi);
-            if (bn >= 0) fbn = ln.fval(bn);
-            continue;
+          int b = n;                                         // its end (exclusive)
+          for (int cc = c; cc < nchunks; ++cc) {
+            const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+            if (w) { b = min(n, (cc << 5) + __ffs(w) - 1); break; }
           }
-          break;
+          const int ca = a >> 5, cb = (b - 1) >> 5;          // the run has boundaries 1 .. cb - ca
+          if (cb - ca >= 2 * half) more = 1;                 // some boundary of it waits for a later round
+          if (((c - ca) & (2 * half - 1)) != half) continue; // not this boundary's round
+          if (half == 1) {
+            // (first round only: later rounds see hulls that earlier merges may have thinned out)
+            // equal-height rows on both sides of the boundary cannot hide one another: when the two
+            // adjacent chunk segments are constant and equal there is nothing to drop here
+            const uint32_t fl_hi = lds_u8_volatile(cflagcol + (uint32_t)c * TX);
+            const uint32_t fl_lo = lds_u8_volatile(cflagcol + (uint32_t)(c - 1) * TX);
+            const bool lo_const = (a >= ((c - 1) << 5)) ? (fl_lo & 2u) != 0 : (fl_lo & 1u) != 0;
+            if ((fl_hi & 1u) && lo_const && ln.fval(i0) == ln.fval(i0 - 1)) continue;
+          }
+          const int alo = max(a, (c - half) << 5);           // the run's rows inside the two groups
+          const int bhi = min(b, min(n, (c + half) << 5));
+          int av = prev_vertex<TX>(ln, i0, alo);
+          int bv = next_vertex<TX>(ln, i0 - 1, bhi);
+          if (av < 0 || bv < 0) continue;
+          int ap = prev_vertex<TX>(ln, av, alo);
+          int bn = next_vertex<TX>(ln, bv, bhi);
+          float fa = ln.fval(av), fb = ln.fval(bv);
+          float fap = ap >= 0 ? ln.fval(ap) : 0.0f, fbn = bn >= 0 ? ln.fval(bn) : 0.0f;
+          for (;;) {
+            if (ap >= 0 && (IntHull ? vertex_hidden_int(ap, fap, av, fa, bv, fb, w2i)
+                                    : vertex_hidden(ap, fap, av, fa, bv, fb, w2d))) {   // A's top is hidden
+              ln.drop(av);
+              av = ap; fa = fap;
+              ap = prev_vertex<TX>(ln, av, alo);
+              if (ap >= 0) fap = ln.fval(ap);
+              continue;
+            }
+            if (bn >= 0 && (IntHull ? vertex_hidden_int(av, fa, bv, fb, bn, fbn, w2i)
+                                    : vertex_hidden(av, fa, bv, fb, bn, fbn, w2d))) {   // B's first is hidden
+              ln.drop(bv);
+              bv = bn; fb = fbn;
+              bn = next_vertex<TX>(ln, bv, bhi);
+              if (bn >= 0) fbn = ln.fval(bn);
+              continue;
+            }
+            break;
+          }
         }
       }
+      if (!__syncthreads_or(more)) break;                    // (the barrier of the round)
     }
-    __syncthreads();
   }
 
   // ============ stage 3: outputs of the crossing segments, ONE loop over their rows per chunk ============
@@ -1042,7 +1123,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       const uint32_t lea_mask = (leaving && wreal) ? (0xffffffffu << s2) : 0u;
 
       HullWalk w;
-      w.a = w.b = 0; w.v = w.v1 = -1; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
+      w.a = w.b = 0; w.v = w.v1 = -1; w.wi = 0; w.rem = 0u; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
       w.lo_b = w.hi_b = false; w.cst = true; w.bg = false;
       for (uint32_t rest = ent_mask | lea_mask; rest; rest &= rest - 1u) {
         const int r = __ffs(rest) - 1;
@@ -1079,8 +1160,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
             const float cand = __fmaf_rn(w2, __fmul_rn(w.dv1, w.dv1), w.fv1);
             if (!(cand <= best)) break;
             best = cand; w.v = w.v1; w.fv = w.fv1; w.dv = w.dv1;
-            w.v1 = next_vertex<TX>(ln, w.v1, w.b);
-            if (w.v1 >= 0) { w.fv1 = ln.fval(w.v1); w.dv1 = (float)(i - w.v1); }
+            walk_advance<TX>(w, ln, i);
           }
           w.dv += 1.0f; w.dv1 += 1.0f;
         }

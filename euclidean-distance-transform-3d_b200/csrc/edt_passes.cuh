@@ -108,7 +108,7 @@ inline void tile_boxes(int n, TileBoxes* tb) {
 
 template <int Bytes, int TX>
 int launch_tile(const void* labels, float* f, LineGeom g, float w2, int border_lo, int border_hi, int flags,
-                bool use_tma, cudaStream_t stream, bool pdl, bool noise) {
+                bool use_tma, cudaStream_t stream, bool pdl, bool noise, bool int_hull) {
   using LT = typename LabelOf<Bytes>::type;
   const int nchunks = (g.n + 31) >> 5;
   TileBoxes tb;
@@ -139,32 +139,37 @@ int launch_tile(const void* labels, float* f, LineGeom g, float w2, int border_l
   cfg.attrs = pdl_attr;
   static const bool pdl_off = getenv("EDTB200_NO_PDL") != nullptr;    // A/B switch for measurements
   cfg.numAttrs = (pdl && !pdl_off) ? 1 : 0;   // only when the previous kernel of the stream is our own pass
+  const int w2i = int_hull ? (int)w2 : 0;
+  static const bool int_off = getenv("EDTB200_NO_INT_HULL") != nullptr;     // A/B switch for measurements
+  // integer hull tests are instantiated for the hot shape only (128-byte rows, TMA staging)
+  const bool ih = int_hull && !int_off && TX == 32 && use_tma;
+#define EDT_LAUNCH_ONE(EPI, TMA, WIDE, CTAS, IH)                                                    \
+  do {                                                                                              \
+    auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, WIDE, CTAS, IH>;                        \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, lab, f, g, tb, w2, border_lo, border_hi, flags, w2i)); \
+  } while (0)
 #define EDT_LAUNCH_TILE(EPI, TMA)                                                                   \
   do {                                                                                              \
-    if (wide) {                                                                                     \
-      auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, true, 3>;                             \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, lab, f, g, tb, w2, border_lo, border_hi, flags)); \
-    } else if (noise && TX == 32) {                                                                 \
-      auto kern = later_axis_tile_kernel<Bytes, TX == 32 ? 32 : TX, EPI, TMA, false, TX == 32 ? 2 : 3>; \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, lab, f, g, tb, w2, border_lo, border_hi, flags)); \
+    if constexpr (TX == 32 && TMA) {                                                                \
+      if (wide) { if (ih) EDT_LAUNCH_ONE(EPI, TMA, true, 3, true); else EDT_LAUNCH_ONE(EPI, TMA, true, 3, false); } \
+      else if (noise) { if (ih) EDT_LAUNCH_ONE(EPI, TMA, false, 2, true); else EDT_LAUNCH_ONE(EPI, TMA, false, 2, false); } \
+      else { if (ih) EDT_LAUNCH_ONE(EPI, TMA, false, 3, true); else EDT_LAUNCH_ONE(EPI, TMA, false, 3, false); } \
     } else {                                                                                        \
-      auto kern = later_axis_tile_kernel<Bytes, TX, EPI, TMA, false, 3>;                            \
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, map, lab, f, g, tb, w2, border_lo, border_hi, flags)); \
+      if (wide) EDT_LAUNCH_ONE(EPI, TMA, true, 3, false); else EDT_LAUNCH_ONE(EPI, TMA, false, 3, false); \
     }                                                                                               \
   } while (0)
   if (flags) { if (use_tma) EDT_LAUNCH_TILE(true, true); else EDT_LAUNCH_TILE(true, false); }
   else       { if (use_tma) EDT_LAUNCH_TILE(false, true); else EDT_LAUNCH_TILE(false, false); }
 #undef EDT_LAUNCH_TILE
+#undef EDT_LAUNCH_ONE
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
 template <int Bytes>
 int launch_later(const void* labels, float* f, const LineGeom& g0, float w, int border_lo, int border_hi,
-                 int flags, DeviceCache& dc, cudaStream_t stream, bool pdl) {
+                 int flags, DeviceCache& dc, cudaStream_t stream, bool pdl, double fmax) {
   using LT = typename LabelOf<Bytes>::type;
   LineGeom g = g0;
   const float w2 = w * w;                       // float product, as src/edt.hpp:181
@@ -185,10 +190,15 @@ int launch_later(const void* labels, float* f, const LineGeom& g0, float w, int 
     if (tx) {
       const bool use_tma = aligned && g.inner_count >= tx;
       const bool noise = noise_predicted(dc);
+      // Integer hull tests: the caller vouches (fmax >= 0) that every finite sample of f is an
+      // integer not above fmax; with an integer w2 and fmax + w2 * n^2 < 2^31 every g = f + w2 v^2
+      // is an exact 32-bit integer.  fmax < 0 = unknown -> double.
+      const bool int_hull = fmax >= 0.0 && w2 == floorf(w2) && w2 >= 1.0f && w2 < 1048576.0f &&
+                            fmax + (double)w2 * (double)g.n * (double)g.n < 2147483000.0;
       switch (tx) {
-        case 32: return launch_tile<Bytes, 32>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, pdl, noise);
-        case 16: return launch_tile<Bytes, 16>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, pdl, noise);
-        default: return launch_tile<Bytes, 8>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, pdl, noise);
+        case 32: return launch_tile<Bytes, 32>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, pdl, noise, int_hull);
+        case 16: return launch_tile<Bytes, 16>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, pdl, noise, int_hull);
+        default: return launch_tile<Bytes, 8>(labels, f, g, w2, border_lo, border_hi, flags, use_tma, stream, pdl, noise, int_hull);
       }
     }
   }
@@ -224,4 +234,5 @@ int launch_later(const void* labels, float* f, const LineGeom& g0, float w, int 
   template int edtb200::host::launch_first<B>(const void*, float*, int64_t, int64_t, float, int, int,    \
                                               edtb200::host::DeviceCache&, cudaStream_t);                \
   template int edtb200::host::launch_later<B>(const void*, float*, const edtb200::LineGeom&, float, int, \
-                                              int, int, edtb200::host::DeviceCache&, cudaStream_t, bool);
+                                              int, int, edtb200::host::DeviceCache&, cudaStream_t, bool, \
+                                              double);
