@@ -49,4 +49,25 @@ check("n > 4096", edt.edtsq(tall), oracle.edtsq(tall))
 # voxel graph
 lab, graph, kw = cases.random_graph_case(7)
 check("voxel graph", edt.edtsq(lab, voxel_graph=graph, **kw), oracle.edtsq(lab, voxel_graph=graph, **kw))
+# the 2-CTA variant of the tile kernel (label noise seen by the previous transform) and the double
+# hull tests (non-integer weights) on long varying runs; a Voronoi-like volume on a 512-row axis
+lab = np.asfortranarray(cases.random_volume(rng, (64, 80, 72), "iid", np.uint32))
+for _ in range(2):
+  got = edt.edtsq(lab)
+check("noise twice", got, oracle.edtsq(lab))
+from scipy.spatial import cKDTree  # noqa: E402
+pts = rng.uniform(0, 1, (12, 3)) * np.array([40, 512, 24])
+grid = np.stack(np.meshgrid(np.arange(40.0), np.arange(512.0), np.arange(24.0), indexing="ij"), -1).reshape(-1, 3)
+vor = np.asfortranarray((cKDTree(pts).query(grid)[1] + 1).astype(np.uint16).reshape(40, 512, 24))
+check("voronoi int", edt.edtsq(vor, anisotropy=(1, 1, 2)), oracle.edtsq(vor, anisotropy=(1, 1, 2)))
+check("voronoi double", edt.edtsq(vor, anisotropy=(0.7, 1.3, 2.9)), oracle.edtsq(vor, anisotropy=(0.7, 1.3, 2.9)))
+# per-label statistics and box-restricted extraction
+import torch  # noqa: E402
+lt = torch.from_numpy(np.ascontiguousarray(vor.astype(np.int32))).cuda()
+dt = edt.edt_cuda(lt, (1.0, 1.0, 1.0), False, sqrt=True)
+st = edt.label_stats_cuda(lt, dt)
+assert int(st["count"].sum().item()) == lt.numel()
+for key, img in edt.each_cuda(lt, dt, in_place=True):
+  assert torch.equal(img, torch.where(lt == key, dt, torch.zeros((), device=dt.device)))
+done += 1
 print("sanitize_cases: %d results equal to the oracle" % done)
