@@ -143,6 +143,29 @@ def host_description():
   return info
 
 
+def bind_to_gpu_numa(local):
+  """Run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers of
+  the end-to-end leg are allocated next to the GPU's PCIe root ('pin with taskset
+  if NUMA').  Returns a description for the JSON line; does nothing when sysfs does not tell."""
+  try:
+    import torch
+    prop = torch.cuda.get_device_properties(local)
+    bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+    with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+      node = int(fh.read().strip())
+    if node < 0:
+      return {"gpu_pci": bdf, "numa_node": node, "bound": False}
+    with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+      cpus = set()
+      for part in fh.read().strip().split(","):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    os.sched_setaffinity(0, cpus)
+    return {"gpu_pci": bdf, "numa_node": node, "bound": True, "cpus": len(cpus)}
+  except Exception as exc:
+    return {"bound": False, "why": repr(exc)}
+
+
 def dist_env():
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -322,6 +345,7 @@ def ours(args):
   import edt_b200
 
   rank, world, local = dist_env()
+  numa = bind_to_gpu_numa(local) if world > 1 else None      # ranks share the host: each next to its GPU
   if world > 1:
     # high-priority NCCL stream: lets the halo exchange run beside the SM-filling Z-pass kernel
     opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
@@ -492,7 +516,50 @@ def ours(args):
     e2e_s = float(te.item())
     e2e = {"value": nvox * world / e2e_s / 1e6, "unit": "Mvoxels/s", "ms_per_step": e2e_s * 1e3,
            "steps": e2e_steps, "h2d_bytes_per_step": nvox * LABEL_BYTES * world,
-           "d2h_bytes_per_step": nvox * 4 * world, "host_memory": "pinned"}
+           "d2h_bytes_per_step": nvox * 4 * world, "host_memory": "pinned", "numa_binding_rank0": numa}
+    # BASELINE configs[4] as written asks for sdf: the same slab step with the sign and sqrt fused, on the
+    # iid slabs and on 32^3 blocks of labels (device-resident, CUDA events, max over ranks)
+    cfg5 = []
+    try:
+      from edt_b200 import workloads
+      blocks, _, _ = workloads.generate("cfg2b", sx, dev, nz=sz * world)
+      blocks = blocks[rank * sz:(rank + 1) * sz].contiguous()
+      # blocks of 32 need a halo that reaches 16 voxels: 32 rows (what method="auto" escalates to)
+      halo32 = None
+      if peer_halo is not None:
+        halo32, _ = ed.make_peer_halo(dev, sy, sx, torch.int32, 32)
+        ok32 = torch.tensor([1 if halo32 is not None else 0], device=dev)
+        dist.all_reduce(ok32, op=dist.ReduceOp.MIN)
+        if int(ok32.item()) == 0:
+          halo32 = None
+      for name, lab, ph in (("iid", labels_dev, peer_halo), ("blocks32", blocks, halo32)):
+        info = {}
+        vs = []
+        def sdf_step():
+          ed.slab_transform(lab, (ANISOTROPY[2], ANISOTROPY[1], ANISOTROPY[0]), False, sqrt=True, signed=True,
+                            passes=passes, info=info, depths=[sz] * world, peer_halo=ph,
+                            defer_check="local" if ph is not None else True)
+          vs.append(info.pop("verdict"))
+        for _ in range(3):
+          sdf_step()
+        ed.check_verdicts(vs)
+        del vs[:]
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(10):
+          sdf_step()
+        e1.record(stream)
+        exact = ed.check_verdicts(vs)
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1) / 10], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        cfg5.append({"labels": name, "function": "sdf", "ms_per_step": float(tt.item()),
+                     "Mvoxels_s": nvox * world / float(tt.item()) / 1e3, "halo_exact": bool(exact),
+                     "method": info.get("method"), "halo_rows": ph.halo if ph is not None else None})
+      del blocks
+    except Exception as exc:
+      cfg5 = {"error": repr(exc)}
     if rank == 0:
       line = {
         "metric": "Mvoxels/s edtsq 512^3 uint32", "value": value, "unit": "Mvoxels/s",
@@ -509,6 +576,7 @@ def ours(args):
                    "timing": "CUDA events on the launch stream, max over ranks"},
         "roofline": roofline, "e2e": e2e, "gpu_launches": (5 if result.get("method") == "halo" else 3) * args.steps,
         "clocks": clocks,
+        "cfg5_sdf": cfg5,
         "parity_checked": parity_checked,
         "parity_check": "before timing: edtsq and sdf of a 512x512x%d volume of 32^3 label blocks (with background, "
                         "anisotropy 2 along z) through the slab split, every rank's slab bit-equal to the same rows "

@@ -698,20 +698,28 @@ __device__ __forceinline__ void read_out_rows_local(const TileLine<TX> ln, int i
                                                     uint32_t ends, uint32_t noncst, uint32_t hb, uint32_t wzero,
                                                     int n, float w2f, bool border_lo, bool border_hi, uint32_t sq,
                                                     char* __restrict__ line0, size_t pitch, int flags) {
+  constexpr uint32_t ROW = TileLine<TX>::ROW;
   const float inf = __int_as_float(0x7f800000);
-  int a = 0, b = 0, v = -1, v1 = -1;
+  int v = -1, v1 = -1;
   bool lo_b = false, hi_b = false, cst = true, bg = false;
   uint32_t left = 0u;
   float fv = inf, fv1 = inf, dv = 0.0f, dv1 = 0.0f;
+  // running addresses of the row at hand (the rows of a run are consecutive): its sample, its two
+  // border terms sq[i - a + 1] / sq[b - i], its output
+  uint32_t f_at = ln.f, sq_lo = sq, sq_hi = sq;
+  char* dst = line0;
   for (uint32_t rest = todo; rest; rest &= rest - 1u) {
     const int r = __ffs(rest) - 1;
-    const int i = i0 + r;
     if ((starts >> r) & 1u) {                                 // first row of a run
       const int e = __ffs(ends & (0xffffffffu << r)) - 1;     // its last row
-      a = i; b = i0 + e + 1;
+      const int a = i0 + r, b = i0 + e + 1;
       lo_b = a > 0 || border_lo; hi_b = b < n || border_hi;
       cst = !((noncst >> r) & 1u);
       bg = (wzero >> r) & 1u;
+      f_at = ln.f + (uint32_t)a * ROW;
+      sq_lo = sq + 4u;
+      sq_hi = sq + (uint32_t)(b - a) * 4u;
+      dst = line0 + (size_t)a * pitch;
       v = v1 = -1; fv = fv1 = inf;
       if (!cst) {
         left = hb & (0xffffffffu << r) & (0xffffffffu >> (31 - e));
@@ -724,7 +732,7 @@ __device__ __forceinline__ void read_out_rows_local(const TileLine<TX> ln, int i
     }
     float best = inf;
     if (cst) {
-      best = ln.fval(i);
+      best = lds_f32(f_at);
     } else if (v >= 0) {
       best = __fmaf_rn(w2f, __fmul_rn(dv, dv), fv);
       while (v1 >= 0) {
@@ -736,10 +744,11 @@ __device__ __forceinline__ void read_out_rows_local(const TileLine<TX> ln, int i
       }
       dv += 1.0f; dv1 += 1.0f;
     }
-    if (lo_b) best = fminf(best, lds_f32(sq + (uint32_t)(i - a + 1) * 4u));
-    if (hi_b) best = fminf(best, lds_f32(sq + (uint32_t)(b - i) * 4u));
+    if (lo_b) best = fminf(best, lds_f32(sq_lo));
+    if (hi_b) best = fminf(best, lds_f32(sq_hi));
     if (Epilogue) best = finish_value(best, bg, flags);       // a run has one label
-    *reinterpret_cast<float*>(line0 + (size_t)i * pitch) = best;
+    *reinterpret_cast<float*>(dst) = best;
+    f_at += ROW; sq_lo += 4u; sq_hi -= 4u; dst += pitch;
   }
 }
 
@@ -1121,6 +1130,50 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       const int s2 = 31 - __clz(wreal | 1u);                            // first row of the last segment
       const uint32_t ent_mask = entering ? (wreal ? ((1u << (__ffs(wreal) - 1)) - 1u) : rowmask) : 0u;
       const uint32_t lea_mask = (leaving && wreal) ? (0xffffffffu << s2) : 0u;
+
+      if (all_const) {
+        // every crossing run of the tile is constant: out = min(f, border terms), a straight loop with
+        // running addresses per segment (solid objects, blocky labels: this is all a pass does there)
+        for (int seg = 0; seg < 2; ++seg) {
+          const uint32_t mask = seg ? lea_mask : ent_mask;
+          if (!mask) continue;
+          const int rlo = __ffs(mask) - 1, rhi = 32 - __clz(mask);      // rows [rlo, rhi) of the chunk
+          int a = i0 + rlo, b;
+          if (!seg) {                                                   // the run started below this chunk
+            a = 0;
+            for (int cc = c - 1; cc >= 0; --cc) {
+              const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
+              if (ws) { a = (cc << 5) + 31 - __clz(ws); break; }
+            }
+          }
+          if (!seg && wreal) {
+            b = i0 + __ffs(wreal) - 1;                                  // ... and ends inside it
+          } else if (leaving) {                                         // the run ends above this chunk
+            b = n;
+            for (int cc = c + 1; cc < nchunks; ++cc) {
+              const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
+              if (ws) { b = min(n, (cc << 5) + __ffs(ws) - 1); break; }
+            }
+          } else {
+            b = min(n, i0 + 32);
+          }
+          const bool lo_b = a > 0 || border_lo, hi_b = b < n || border_hi, bg = (wzero >> rlo) & 1u;
+          uint32_t f_at = ln.f + (uint32_t)(i0 + rlo) * ROW;
+          uint32_t sq_lo = sq_t + (uint32_t)(i0 + rlo - a + 1) * 4u;   // sq[i - a + 1]
+          uint32_t sq_hi = sq_t + (uint32_t)(b - i0 - rlo) * 4u;       // sq[b - i]
+          char* dst = line0 + (size_t)(i0 + rlo) * pitch;
+#pragma unroll 4
+          for (int r = rlo; r < rhi; ++r) {
+            float best = lds_f32(f_at);
+            if (lo_b) best = fminf(best, lds_f32(sq_lo));
+            if (hi_b) best = fminf(best, lds_f32(sq_hi));
+            if (Epilogue) best = finish_value(best, bg, flags);
+            *reinterpret_cast<float*>(dst) = best;
+            f_at += ROW; sq_lo += 4u; sq_hi -= 4u; dst += pitch;
+          }
+        }
+        continue;
+      }
 
       HullWalk w;
       w.a = w.b = 0; w.v = w.v1 = -1; w.wi = 0; w.rem = 0u; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
