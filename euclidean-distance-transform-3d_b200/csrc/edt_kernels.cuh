@@ -782,14 +782,13 @@ __device__ __forceinline__ void walk_advance(HullWalk& w, const TileLine<TX> ln,
 // starting at the nearest vertex at or below lo (else the first one above) and descending along
 // the hull -- at a fixed row the candidate values are unimodal.
 template <int TX>
-__device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, uint32_t cflagcol, int lo, int a, int b,
-                                           int n, float w2f, bool border_lo, bool border_hi, bool background,
-                                           bool all_const) {
+__device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, int lo, int a, int b, int n, float w2f,
+                                           bool border_lo, bool border_hi, bool background, bool constant) {
   const float inf = __int_as_float(0x7f800000);
   w.a = a; w.b = b;
   w.lo_b = a > 0 || border_lo; w.hi_b = b < n || border_hi;
   w.bg = background;
-  w.cst = all_const || run_is_constant<TX>(ln, cflagcol, a, b);
+  w.cst = constant;
   w.v = w.v1 = -1; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
   w.wi = 0; w.rem = 0u;
   if (w.cst) return;
@@ -1131,32 +1130,32 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       const uint32_t ent_mask = entering ? (wreal ? ((1u << (__ffs(wreal) - 1)) - 1u) : rowmask) : 0u;
       const uint32_t lea_mask = (leaving && wreal) ? (0xffffffffu << s2) : 0u;
 
-      if (all_const) {
-        // every crossing run of the tile is constant: out = min(f, border terms), a straight loop with
-        // running addresses per segment (solid objects, blocky labels: this is all a pass does there)
+      // the runs of the two segments: [a_ent, b_ent) came in from below, [i0 + s2, b_up) leaves above
+      int a_ent = 0, b_up = n;
+      if (entering) {
+        for (int cc = c - 1; cc >= 0; --cc) {
+          const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
+          if (ws) { a_ent = (cc << 5) + 31 - __clz(ws); break; }
+        }
+      }
+      if (leaving) {
+        for (int cc = c + 1; cc < nchunks; ++cc) {
+          const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
+          if (ws) { b_up = min(n, (cc << 5) + __ffs(ws) - 1); break; }
+        }
+      }
+      const int b_ent = wreal ? (i0 + __ffs(wreal) - 1) : (leaving ? b_up : min(n, i0 + 32));
+      const bool cst_ent = ent_mask && (all_const || run_is_constant<TX>(ln, cflagcol, a_ent, b_ent));
+      const bool cst_lea = lea_mask && (all_const || run_is_constant<TX>(ln, cflagcol, i0 + s2, b_up));
+
+      if ((!ent_mask || cst_ent) && (!lea_mask || cst_lea)) {
+        // every crossing run of this chunk is constant: out = min(f, border terms), a straight loop with
+        // running addresses per segment (solid objects, blocky labels, background: all a pass does there)
         for (int seg = 0; seg < 2; ++seg) {
           const uint32_t mask = seg ? lea_mask : ent_mask;
           if (!mask) continue;
           const int rlo = __ffs(mask) - 1, rhi = 32 - __clz(mask);      // rows [rlo, rhi) of the chunk
-          int a = i0 + rlo, b;
-          if (!seg) {                                                   // the run started below this chunk
-            a = 0;
-            for (int cc = c - 1; cc >= 0; --cc) {
-              const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
-              if (ws) { a = (cc << 5) + 31 - __clz(ws); break; }
-            }
-          }
-          if (!seg && wreal) {
-            b = i0 + __ffs(wreal) - 1;                                  // ... and ends inside it
-          } else if (leaving) {                                         // the run ends above this chunk
-            b = n;
-            for (int cc = c + 1; cc < nchunks; ++cc) {
-              const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
-              if (ws) { b = min(n, (cc << 5) + __ffs(ws) - 1); break; }
-            }
-          } else {
-            b = min(n, i0 + 32);
-          }
+          const int a = seg ? i0 + s2 : a_ent, b = seg ? b_up : b_ent;
           const bool lo_b = a > 0 || border_lo, hi_b = b < n || border_hi, bg = (wzero >> rlo) & 1u;
           uint32_t f_at = ln.f + (uint32_t)(i0 + rlo) * ROW;
           uint32_t sq_lo = sq_t + (uint32_t)(i0 + rlo - a + 1) * 4u;   // sq[i - a + 1]
@@ -1182,27 +1181,9 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
         const int r = __ffs(rest) - 1;
         const int i = i0 + r;
         if (r == 0 || (lea_mask && r == s2)) {                          // first row of a segment: set the walk up
-          int a = i, b;
-          if (r == 0 && entering) {                                     // the run started below this chunk
-            a = 0;
-            for (int cc = c - 1; cc >= 0; --cc) {
-              const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
-              if (ws) { a = (cc << 5) + 31 - __clz(ws); break; }
-            }
-          }
-          if (r == 0 && entering && wreal) {
-            b = i0 + __ffs(wreal) - 1;                                  // ... and ends inside it
-          } else if (leaving) {                                         // the run ends above this chunk
-            b = n;
-            for (int cc = c + 1; cc < nchunks; ++cc) {
-              const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
-              if (ws) { b = min(n, (cc << 5) + __ffs(ws) - 1); break; }
-            }
-          } else {
-            b = min(n, i0 + 32);
-          }
-          walk_begin<TX>(w, ln, cflagcol, i, a, b, n, w2, border_lo != 0, border_hi != 0, (wzero >> r) & 1u,
-                         all_const);
+          const bool first = r == 0 && entering;
+          walk_begin<TX>(w, ln, i, first ? a_ent : i, first ? b_ent : b_up, n, w2, border_lo != 0, border_hi != 0,
+                         (wzero >> r) & 1u, first ? cst_ent : cst_lea);
         }
         float best = inf;
         if (w.cst) {
