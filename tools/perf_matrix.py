@@ -32,10 +32,14 @@ def main():
   ap.add_argument("--only", default="cfg2,cfg2b,blocks8,cfg3,balls,voronoi,ones_nobb")
   ap.add_argument("--steps", type=int, default=5)
   ap.add_argument("--sqrt", action="store_true")
+  ap.add_argument("--aniso", default=None, help="w_z,w_y,w_x overriding the workload's anisotropy (e.g. a "
+                  "non-integer one, which takes the double-precision hull tests)")
   args = ap.parse_args()
   dev = torch.device("cuda", 0)
   for name in args.only.split(","):
     lab, an, bb = gen(name, args.size, dev)
+    if args.aniso:
+      an = tuple(float(v) for v in args.aniso.split(","))
     out = torch.empty(lab.shape, dtype=torch.float32, device=dev)
     for _ in range(2):
       edt_b200.edt_cuda(lab, an, bb, sqrt=args.sqrt, out=out)
