@@ -1191,7 +1191,7 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
   // Z pass on the slab, interior faces open
   nvtx_push("edt.z");
   rc = dispatch_later(label_bytes, labels_dev, f_dev, gz, wz, border && !has_lo, border && !has_hi, epilogue, *dc,
-                      stream, /*pdl=*/false, integer_bound(ws, ns, 2));
+                      stream, /*pdl=*/!verbose && (has_lo || has_hi), integer_bound(ws, ns, 2));
   nvtx_pop();
   if (rc) return rc;
 
@@ -1205,10 +1205,17 @@ int edtb200_slab_step(const void* labels_dev, int label_bytes, int64_t sx, int64
     const unsigned char* set_hi = has_hi ? hi + (size_t)parity * L.set_bytes : nullptr;
     const unsigned long long* flag_from_lo = reinterpret_cast<const unsigned long long*>(self + L.flag_from_lo);
     const unsigned long long* flag_from_hi = reinterpret_cast<const unsigned long long*>(self + L.flag_from_hi);
+    cudaLaunchConfig_t fcfg = {};
+    fcfg.gridDim = grid; fcfg.blockDim = dim3(256); fcfg.dynamicSmemBytes = 0; fcfg.stream = stream;
+    cudaLaunchAttribute fattr[1];
+    fattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    fattr[0].val.programmaticStreamSerializationAllowed = 1;
+    fcfg.attrs = fattr;
+    fcfg.numAttrs = verbose ? 0 : 1;         // behind our own Z pass, which triggers its dependents early
 #define EDT_FIXUP(B, T)                                                                                          \
-    slab_fixup_kernel<B><<<grid, 256, 0, stream>>>(static_cast<const T*>(labels_dev), f_dev, plane, (int)sz, halo, w2, \
-                                                   has_lo, has_hi, set_lo, set_hi, L, step, flag_from_lo, flag_from_hi, \
-                                                   kflags, status_dev)
+    CUDA_TRY(cudaLaunchKernelEx(&fcfg, slab_fixup_kernel<B>, static_cast<const T*>(labels_dev), f_dev, plane, (int)sz, \
+                                halo, w2, has_lo, has_hi, set_lo, set_hi, L, step, flag_from_lo, flag_from_hi, kflags, \
+                                status_dev))
     switch (label_bytes) {
       case 1: EDT_FIXUP(1, uint8_t); break;
       case 2: EDT_FIXUP(2, uint16_t); break;

@@ -70,6 +70,7 @@ slab_stage_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, cons
                   SlabStageLayout L, unsigned long long step, unsigned long long* flag_in_lo_peer,
                   unsigned long long* flag_in_hi_peer, unsigned int* counter) {
   using LT = typename LabelOf<Bytes>::type;
+  pdl_launch_dependents();                 // the Z pass may start staging its labels under this kernel
   const int face = blockIdx.y;
   const bool active = face == 0 ? has_lo != 0 : has_hi != 0;
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,6 +118,8 @@ slab_fixup_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, floa
   using LT = typename LabelOf<Bytes>::type;
   const int high_face = blockIdx.y;
   if (high_face == 0 ? !has_lo : !has_hi) return;
+  // launched with programmatic stream serialization right behind the Z pass: the CTAs become
+  // resident during its last wave, wait for the neighbour's flag, and only then for the Z pass
   __shared__ int ready;
   if (threadIdx.x == 0) {
     const unsigned long long* flag = high_face ? flag_from_hi : flag_from_lo;
@@ -128,6 +131,7 @@ slab_fixup_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, floa
     ready = ok;
   }
   __syncthreads();
+  pdl_wait_for_previous_grid();            // f holds the Z pass's results from here on
   if (!ready) {
     if (threadIdx.x == 0) atomicOr(status, 2);
     return;
