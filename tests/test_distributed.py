@@ -239,6 +239,77 @@ def test_slab_split_matches_single_volume(world):
   assert any(m == "halo" for _, m in used) and any(m == "transpose" for _, m in used), used
 
 
+def _deferred_worker(rank, world, port, queue):
+  """defer_check=True / "local": verdicts are collected over a batch of steps and read once."""
+  sys.path.insert(0, ROOT)
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    import edt_b200.distributed as ed
+
+    def step(idx, mode):
+      shape, kind, an, bb, sqrt, signed, _ = CASES[idx]
+      z0, zc = ed.split_extent(shape[0], world)[rank]
+      local = torch.from_numpy(_volume(CASES[idx])[z0:z0 + zc].copy())
+      info = {}
+      out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed, passes=OraclePasses(), halo=2, info=info,
+                              defer_check=mode)
+      assert info["method"] == "halo"
+      return idx, z0, out.numpy(), info["verdict"]
+
+    report = {}
+    for mode in (True, "local"):
+      clean = [step(idx, mode) for idx in (7, 8, 9, 10, 11)]      # the halo is exact for these
+      report[("clean", mode)] = ed.check_verdicts([v for *_, v in clean])
+      dirty = clean[:2] + [step(12, mode)]                        # ... and one step where it is not
+      report[("dirty", mode)] = ed.check_verdicts([v for *_, v in dirty])
+      if mode == "local":
+        assert all(work is None for *_, (flag, work) in clean)    # no collective inside the steps
+        for idx, z0, arr, _ in clean:
+          queue.put((idx, rank, z0, arr))
+    queue.put(("report", rank, report))
+  except Exception:
+    import traceback
+    queue.put(("error", rank, traceback.format_exc()))
+    raise
+  finally:
+    dist.destroy_process_group()
+
+
+def test_deferred_verdicts_are_combined_once_per_batch():
+  sys.path.insert(0, ROOT)
+  from oracle import oracle
+  world = 2
+  ctx = mp.get_context("spawn")
+  queue = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_deferred_worker, args=(r, world, port, queue)) for r in range(world)]
+  for p in procs:
+    p.start()
+  items = []
+  for _ in range(world * 6):
+    item = queue.get(timeout=300)
+    assert item[0] != "error", item
+    items.append(item)
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  reports = [it[2] for it in items if it[0] == "report"]
+  assert len(reports) == world
+  for rep in reports:                    # every rank reaches the same conclusion
+    assert rep == {("clean", True): True, ("dirty", True): False, ("clean", "local"): True, ("dirty", "local"): False}
+  for idx in (7, 8, 9, 10, 11):
+    shape, kind, an, bb, sqrt, signed, _ = CASES[idx]
+    fn = {(False, False): oracle.edtsq, (True, False): oracle.edt,
+          (False, True): oracle.sdfsq, (True, True): oracle.sdf}[(sqrt, signed)]
+    got = np.zeros(shape, dtype=np.float32)
+    for it in items:
+      if it[0] == idx:
+        got[it[2]:it[2] + it[3].shape[0]] = it[3]
+    assert np.array_equal(got, fn(_volume(CASES[idx]), anisotropy=an, black_border=bb), equal_nan=True), idx
+
+
 def test_split_extent():
   sys.path.insert(0, ROOT)
   import edt_b200.distributed as ed
