@@ -51,7 +51,8 @@ EncodeTiledFn tensor_map_encoder() {
 size_t tile_smem_bytes(int n, int tx, int rows_alloc) {
   const int nchunks = (n + 31) >> 5;
   return (size_t)rows_alloc * tx * 4 + (size_t)nchunks * tx * 12 + (size_t)((n + 3) & ~1) * 4 + 16 +
-         (size_t)nchunks * tx;     // + one flag byte per (chunk, line)
+         (size_t)nchunks * tx +    // + one flag byte per (chunk, line)
+         (size_t)tx * 4 + 4;       // + one word per line: chunks holding a run start
 }
 
 // Will launch_later() take the shared-memory tile kernel for this geometry?  (same conditions)

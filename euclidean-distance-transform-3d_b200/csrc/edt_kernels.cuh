@@ -488,6 +488,9 @@ __device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_shared_or(uint32_t addr, uint32_t bits) {
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
+}
 // Zero that the compiler cannot see through, produced at this point of the program order.
 __device__ __forceinline__ uint32_t smem_token() {
   uint32_t t;
@@ -756,10 +759,9 @@ __device__ __forceinline__ void read_out_rows_local(const TileLine<TX> ln, int i
 // rows of one chunk: current vertex v, next vertex v1, and an iterator over the vertices above v1
 // (`rem` = the not yet visited vertex bits of hull word `wi`, clipped to the run in its last word).
 struct HullWalk {
-  int a, b, v, v1, wi;
+  int b, v, v1, wi;
   uint32_t rem;
   float fv, fv1, dv, dv1;
-  bool lo_b, hi_b, cst, bg;
 };
 
 // v1 <- the next vertex of the run above the current v1 (or -1), and its sample.
@@ -782,16 +784,11 @@ __device__ __forceinline__ void walk_advance(HullWalk& w, const TileLine<TX> ln,
 // starting at the nearest vertex at or below lo (else the first one above) and descending along
 // the hull -- at a fixed row the candidate values are unimodal.
 template <int TX>
-__device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, int lo, int a, int b, int n, float w2f,
-                                           bool border_lo, bool border_hi, bool background, bool constant) {
+__device__ __forceinline__ void walk_begin(HullWalk& w, const TileLine<TX> ln, int lo, int a, int b, float w2f) {
   const float inf = __int_as_float(0x7f800000);
-  w.a = a; w.b = b;
-  w.lo_b = a > 0 || border_lo; w.hi_b = b < n || border_hi;
-  w.bg = background;
-  w.cst = constant;
+  w.b = b;
   w.v = w.v1 = -1; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
   w.wi = 0; w.rem = 0u;
-  if (w.cst) return;
   int v = prev_vertex<TX>(ln, lo + 1, a);
   if (v < 0) v = next_vertex<TX>(ln, lo, b);
   if (v >= 0) {
@@ -843,7 +840,9 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   const uint32_t hullw_a = zerow_a + (uint32_t)nchunks * ROW;           // u32   [nchunks][TX]
   const uint32_t sq_a = hullw_a + (uint32_t)nchunks * ROW;              // float [n + 2]
   const uint32_t bar_a = sq_a + (uint32_t)((n + 2 + 1) & ~1) * 4u;      // mbarrier
-  const uint32_t cflag_a = bar_a + 16u;                                 // u8    [nchunks][TX]
+  const uint32_t nz_a = bar_a + 16u;                                    // u32   [TX]: chunks holding a run start
+  const uint32_t cflag_a = nz_a + TX * 4u;                              // u8    [nchunks][TX]
+  const bool use_nz = nchunks <= 32;                                    // (one bit per chunk; longer lines search)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_tile + (bar_a - fs_a));
 
   const int lane = threadIdx.x & 31;
@@ -874,6 +873,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   }
 
   // ============ stage 0: labels -> run-start / background words; border-term table ============
+  if (threadIdx.x < TX) sts_u32(nz_a + threadIdx.x * 4u, 0u);
   for (int i = threadIdx.x; i < n + 2; i += blockDim.x) {
     const float e = (float)i;
     sts_f32(sq_a + (uint32_t)i * 4u, __fmul_rn(w2, __fmul_rn(e, e)));
@@ -927,6 +927,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   // per (chunk, line): bit 0 = the long-run segment entering from below is constant,
   //                    bit 1 = the long-run segment leaving above is constant
   const uint32_t cflagcol = cflag_a + (uint32_t)x;
+  const uint32_t nzcol = nz_a + (uint32_t)x * 4u;
   char* const line0 = reinterpret_cast<char*>(tf + x);
 
   // ============ stage 1: everything that can be finished inside a chunk ============
@@ -1031,6 +1032,14 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
     }
   }
   if (!__syncthreads_or(any_cross)) return;                // every run was finished inside its chunk
+  // Tiles with crossing runs: one bit per chunk that holds a run start, per line, so that the ends
+  // of a crossing run are two look-ups instead of a walk over the chunks (made visible by the vote below).
+  if (live && use_nz) {
+    for (int c = chunk0; c < nchunks; c += chunk_step) {
+      const uint32_t rowmask = (n - (c << 5) >= 32) ? 0xffffffffu : ((1u << (n - (c << 5))) - 1u);
+      if (lds_u32(startcol + (uint32_t)c * ROW) & rowmask) red_shared_or(nzcol, 1u << c);
+    }
+  }
   // every crossing run of the tile constant (blocky labels, solid objects along this axis)?  Then
   // nothing needs stitching and stage 3 writes min(f, border terms) without looking at any hull.
   const bool all_const = !__syncthreads_or(any_cross & 2);
@@ -1058,14 +1067,27 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           const uint32_t wc = lds_u32(startcol + (uint32_t)c * ROW);
           if (wc & 1u) continue;                             // a run starts exactly here: nothing crosses
           int a = 0;                                         // start of the run that crosses
-          for (int cc = c - 1; cc >= 0; --cc) {
-            const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
-            if (w) { a = (cc << 5) + 31 - __clz(w); break; }
-          }
           int b = n;                                         // its end (exclusive)
-          for (int cc = c; cc < nchunks; ++cc) {
-            const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
-            if (w) { b = min(n, (cc << 5) + __ffs(w) - 1); break; }
+          if (use_nz) {
+            const uint32_t nzw = lds_u32_volatile(nzcol);
+            const uint32_t below = nzw & ((1u << c) - 1u), above = nzw & (0xffffffffu << c);
+            if (below) {
+              const int cc = 31 - __clz(below);
+              a = (cc << 5) + 31 - __clz(lds_u32(startcol + (uint32_t)cc * ROW));
+            }
+            if (above) {
+              const int cc = __ffs(above) - 1;
+              b = min(n, (cc << 5) + __ffs(lds_u32(startcol + (uint32_t)cc * ROW)) - 1);
+            }
+          } else {
+            for (int cc = c - 1; cc >= 0; --cc) {
+              const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+              if (w) { a = (cc << 5) + 31 - __clz(w); break; }
+            }
+            for (int cc = c; cc < nchunks; ++cc) {
+              const uint32_t w = lds_u32(startcol + (uint32_t)cc * ROW);
+              if (w) { b = min(n, (cc << 5) + __ffs(w) - 1); break; }
+            }
           }
           const int ca = a >> 5, cb = (b - 1) >> 5;          // the run has boundaries 1 .. cb - ca
           if (cb - ca >= 2 * half) more = 1;                 // some boundary of it waits for a later round
@@ -1132,35 +1154,63 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
 
       // the runs of the two segments: [a_ent, b_ent) came in from below, [i0 + s2, b_up) leaves above
       int a_ent = 0, b_up = n;
-      if (entering) {
-        for (int cc = c - 1; cc >= 0; --cc) {
-          const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
-          if (ws) { a_ent = (cc << 5) + 31 - __clz(ws); break; }
+      if (use_nz) {                  // nearest chunks with a run start, from the line's chunk mask
+        const uint32_t nzw = lds_u32_volatile(nzcol);
+        const uint32_t below = entering ? (nzw & ((1u << c) - 1u)) : 0u;
+        const uint32_t above = leaving ? (nzw & (0xfffffffeu << c)) : 0u;
+        if (below) {
+          const int cc = 31 - __clz(below);
+          a_ent = (cc << 5) + 31 - __clz(lds_u32(startcol + (uint32_t)cc * ROW));
         }
-      }
-      if (leaving) {
-        for (int cc = c + 1; cc < nchunks; ++cc) {
-          const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
-          if (ws) { b_up = min(n, (cc << 5) + __ffs(ws) - 1); break; }
+        if (above) {
+          const int cc = __ffs(above) - 1;
+          b_up = min(n, (cc << 5) + __ffs(lds_u32(startcol + (uint32_t)cc * ROW)) - 1);
+        }
+      } else {
+        if (entering) {
+          for (int cc = c - 1; cc >= 0; --cc) {
+            const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
+            if (ws) { a_ent = (cc << 5) + 31 - __clz(ws); break; }
+          }
+        }
+        if (leaving) {
+          for (int cc = c + 1; cc < nchunks; ++cc) {
+            const uint32_t ws = lds_u32(startcol + (uint32_t)cc * ROW);
+            if (ws) { b_up = min(n, (cc << 5) + __ffs(ws) - 1); break; }
+          }
         }
       }
       const int b_ent = wreal ? (i0 + __ffs(wreal) - 1) : (leaving ? b_up : min(n, i0 + 32));
       const bool cst_ent = ent_mask && (all_const || run_is_constant<TX>(ln, cflagcol, a_ent, b_ent));
       const bool cst_lea = lea_mask && (all_const || run_is_constant<TX>(ln, cflagcol, i0 + s2, b_up));
 
-      if ((!ent_mask || cst_ent) && (!lea_mask || cst_lea)) {
-        // every crossing run of this chunk is constant: out = min(f, border terms), a straight loop with
-        // running addresses per segment (solid objects, blocky labels, background: all a pass does there)
-        for (int seg = 0; seg < 2; ++seg) {
-          const uint32_t mask = seg ? lea_mask : ent_mask;
-          if (!mask) continue;
-          const int rlo = __ffs(mask) - 1, rhi = 32 - __clz(mask);      // rows [rlo, rhi) of the chunk
-          const int a = seg ? i0 + s2 : a_ent, b = seg ? b_up : b_ent;
-          const bool lo_b = a > 0 || border_lo, hi_b = b < n || border_hi, bg = (wzero >> rlo) & 1u;
+      // one straight loop per crossing segment (the rows of a segment are adjacent), running addresses
+      for (int seg = 0; seg < 2; ++seg) {
+        const uint32_t mask = seg ? lea_mask : ent_mask;
+        if (!mask) continue;
+        const int rlo = __ffs(mask) - 1, rhi = 32 - __clz(mask);      // rows [rlo, rhi) of the chunk
+        const int a = seg ? i0 + s2 : a_ent, b = seg ? b_up : b_ent;
+        const bool cst = seg ? cst_lea : cst_ent;
+        const bool lo_b = a > 0 || border_lo, hi_b = b < n || border_hi, bg = (wzero >> rlo) & 1u;
+        uint32_t sq_lo = sq_t + (uint32_t)(i0 + rlo - a + 1) * 4u;   // sq[i - a + 1]
+        uint32_t sq_hi = sq_t + (uint32_t)(b - i0 - rlo) * 4u;       // sq[b - i]
+        char* dst = line0 + (size_t)(i0 + rlo) * pitch;
+        if (cst) {
+          // a constant run: out = min(f, border terms) (solid objects, blocky labels, background).
+          // The run's one value against the smallest border terms these rows can see (those of the
+          // rows nearest to a and to b): when it is not above them every row keeps its value, and as
+          // the pass works in place nothing has to be stored at all
           uint32_t f_at = ln.f + (uint32_t)(i0 + rlo) * ROW;
-          uint32_t sq_lo = sq_t + (uint32_t)(i0 + rlo - a + 1) * 4u;   // sq[i - a + 1]
-          uint32_t sq_hi = sq_t + (uint32_t)(b - i0 - rlo) * 4u;       // sq[b - i]
-          char* dst = line0 + (size_t)(i0 + rlo) * pitch;
+          const float f0 = lds_f32(f_at);
+          const float lo_min = lo_b ? lds_f32(sq_lo) : inf;
+          const float hi_min = hi_b ? lds_f32(sq_t + (uint32_t)(b - i0 - rhi + 1) * 4u) : inf;
+          if (f0 <= fminf(lo_min, hi_min)) {
+            if (!Epilogue) continue;
+            const float v = finish_value(f0, bg, flags);
+            if (__float_as_uint(v) == __float_as_uint(f0)) continue;
+            for (int r = rlo; r < rhi; ++r) { *reinterpret_cast<float*>(dst) = v; dst += pitch; }
+            continue;
+          }
 #pragma unroll 4
           for (int r = rlo; r < rhi; ++r) {
             float best = lds_f32(f_at);
@@ -1170,38 +1220,28 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
             *reinterpret_cast<float*>(dst) = best;
             f_at += ROW; sq_lo += 4u; sq_hi -= 4u; dst += pitch;
           }
+          continue;
         }
-        continue;
-      }
-
-      HullWalk w;
-      w.a = w.b = 0; w.v = w.v1 = -1; w.wi = 0; w.rem = 0u; w.fv = w.fv1 = inf; w.dv = w.dv1 = 0.0f;
-      w.lo_b = w.hi_b = false; w.cst = true; w.bg = false;
-      for (uint32_t rest = ent_mask | lea_mask; rest; rest &= rest - 1u) {
-        const int r = __ffs(rest) - 1;
-        const int i = i0 + r;
-        if (r == 0 || (lea_mask && r == s2)) {                          // first row of a segment: set the walk up
-          const bool first = r == 0 && entering;
-          walk_begin<TX>(w, ln, i, first ? a_ent : i, first ? b_ent : b_up, n, w2, border_lo != 0, border_hi != 0,
-                         (wzero >> r) & 1u, first ? cst_ent : cst_lea);
-        }
-        float best = inf;
-        if (w.cst) {
-          best = ln.fval(i);
-        } else if (w.v >= 0) {
-          best = __fmaf_rn(w2, __fmul_rn(w.dv, w.dv), w.fv);
-          while (w.v1 >= 0) {
-            const float cand = __fmaf_rn(w2, __fmul_rn(w.dv1, w.dv1), w.fv1);
-            if (!(cand <= best)) break;
-            best = cand; w.v = w.v1; w.fv = w.fv1; w.dv = w.dv1;
-            walk_advance<TX>(w, ln, i);
+        HullWalk w;
+        walk_begin<TX>(w, ln, i0 + rlo, a, b, w2);
+        for (int i = i0 + rlo; i < i0 + rhi; ++i) {
+          float best = inf;
+          if (w.v >= 0) {
+            best = __fmaf_rn(w2, __fmul_rn(w.dv, w.dv), w.fv);
+            while (w.v1 >= 0) {
+              const float cand = __fmaf_rn(w2, __fmul_rn(w.dv1, w.dv1), w.fv1);
+              if (!(cand <= best)) break;
+              best = cand; w.v = w.v1; w.fv = w.fv1; w.dv = w.dv1;
+              walk_advance<TX>(w, ln, i);
+            }
+            w.dv += 1.0f; w.dv1 += 1.0f;
           }
-          w.dv += 1.0f; w.dv1 += 1.0f;
+          if (lo_b) best = fminf(best, lds_f32(sq_lo));
+          if (hi_b) best = fminf(best, lds_f32(sq_hi));
+          if (Epilogue) best = finish_value(best, bg, flags);             // a run has one label
+          *reinterpret_cast<float*>(dst) = best;
+          sq_lo += 4u; sq_hi -= 4u; dst += pitch;
         }
-        if (w.lo_b) best = fminf(best, lds_f32(sq_t + (uint32_t)(i - w.a + 1) * 4u));
-        if (w.hi_b) best = fminf(best, lds_f32(sq_t + (uint32_t)(w.b - i) * 4u));
-        if (Epilogue) best = finish_value(best, w.bg, flags);           // a run has one label
-        *reinterpret_cast<float*>(line0 + (size_t)i * pitch) = best;
       }
     }
   }
