@@ -828,6 +828,9 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   using LT = typename LabelOf<Bytes>::type;
   extern __shared__ __align__(128) unsigned char smem_tile[];
   constexpr int SUBS = 32 / TX;                       // chunks handled side by side by one warp
+  // Variants with registers to spare (2 CTAs per SM, or one wide CTA) step a 64-bit label pointer
+  // and share one pass over the samples between (1a) and (1b); at 40 registers both cost spills.
+  constexpr bool kRoomy = Wide || MinCtas == 2;
   constexpr uint32_t ROW = TX * 4;                    // bytes between rows of fs / between words
 
   const int n = g.n;
@@ -883,23 +886,26 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
     uint32_t wstart = 0, wzero = 0;
     if (live) {
       uint32_t idx = (uint32_t)i0 * ls + (uint32_t)x;
+      const LT* lp = tl + idx;               // (kRoomy) stepped by one line stride per row
       LT prev = (i0 > 0) ? tl[idx - ls] : (LT)0;
       uint32_t fdst = fs_a + (uint32_t)i0 * ROW + (uint32_t)x * 4u;
       if (i0 + 32 <= n) {
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
-          const LT here = tl[idx];
+          const LT here = kRoomy ? *lp : tl[idx];
+          if (kRoomy) lp += ls;
           if (!UseTMA) sts_f32(fdst + r * ROW, tf[idx]);
-          idx += ls;
+          if (!UseTMA || !kRoomy) idx += ls;
           if (here != prev) wstart |= (1u << r);
           if (Epilogue && here == 0) wzero |= (1u << r);
           prev = here;
         }
       } else {
         for (int r = 0; r < n - i0; ++r) {
-          const LT here = tl[idx];
+          const LT here = kRoomy ? *lp : tl[idx];
+          if (kRoomy) lp += ls;
           if (!UseTMA) sts_f32(fdst + r * ROW, tf[idx]);
-          idx += ls;
+          if (!UseTMA || !kRoomy) idx += ls;
           if (here != prev) wstart |= (1u << r);
           if (Epilogue && here == 0) wzero |= (1u << r);
           prev = here;
@@ -955,30 +961,68 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       if (!border_lo && c == 0) single &= ~1u;             // rows lacking a border term go the long way
       if (!border_hi && i0 + 32 >= n) single &= ~(1u << (n - 1 - i0));
 
-      // (1a) runs of length one: value computed unconditionally, store predicated
-      if (single) {
-        const uint32_t fp0 = ln.f + (uint32_t)i0 * ROW;
-        char* const op0 = line0 + (size_t)i0 * pitch;
-        if (rows == 32) {
-          char* op = op0;
+      // (1a) runs of length one: out = min(f, w2).  The pass works in place, so a row that keeps its
+      // value (f <= w2 -- with label noise nearly every row of the later passes) is not stored at
+      // all: one pass over the chunk's samples marks the rows that change (`chg`) and, for (1b),
+      // the rows whose sample differs from the row below (`breaks`).  The square root / sign of the
+      // last pass rewrites every row.
+      uint32_t breaks = 0u;
+      bool have_breaks = false;
+      const uint32_t multi = rowmask & ~single;
+      {
+        const uint32_t at = ln.f + (uint32_t)i0 * ROW;
+        if (single && !Epilogue && kRoomy) {
+          have_breaks = true;
+          uint32_t chg = 0u;
+          float prev = lds_f32(at);
+          if (prev > w2) chg = 1u;
+          if (rows == 32) {
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            float v = fminf(lds_f32(fp0 + r * ROW), w2);
-            if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
-            if (single & (1u << r)) *reinterpret_cast<float*>(op) = v;
-            op += pitch;
+            for (int r = 1; r < 32; ++r) {
+              const float cur = lds_f32(at + r * ROW);
+              if (cur != prev) breaks |= 1u << r;
+              if (cur > w2) chg |= 1u << r;
+              prev = cur;
+            }
+          } else {
+            for (int r = 1; r < rows; ++r) {
+              const float cur = lds_f32(at + r * ROW);
+              if (cur != prev) breaks |= 1u << r;
+              if (cur > w2) chg |= 1u << r;
+              prev = cur;
+            }
           }
+          for (chg &= single; chg; chg &= chg - 1u)
+            *reinterpret_cast<float*>(line0 + (size_t)(i0 + __ffs(chg) - 1) * pitch) = w2;
         } else {
-          for (int r = 0; r < rows; ++r) {
-            float v = fminf(lds_f32(fp0 + r * ROW), w2);
-            if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
-            if (single & (1u << r)) *reinterpret_cast<float*>(op0 + (size_t)r * pitch) = v;
+          if (single) {                     // value computed unconditionally, store predicated
+            char* op = line0 + (size_t)i0 * pitch;
+            if (rows == 32) {
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const float fv = lds_f32(at + r * ROW);
+                if (Epilogue) {
+                  const float v = finish_value(fminf(fv, w2), (wzero >> r) & 1u, flags);
+                  if (single & (1u << r)) *reinterpret_cast<float*>(op) = v;
+                } else {
+                  if ((single & (1u << r)) && fv > w2) *reinterpret_cast<float*>(op) = w2;
+                }
+                op += pitch;
+              }
+            } else {
+              for (int r = 0; r < rows; ++r) {
+                const float fv = lds_f32(at + r * ROW);
+                float v = fminf(fv, w2);
+                if (Epilogue) v = finish_value(v, (wzero >> r) & 1u, flags);
+                if ((single & (1u << r)) && (Epilogue || fv > w2)) *reinterpret_cast<float*>(op) = v;
+                op += pitch;
+              }
+            }
           }
         }
       }
 
       uint32_t hb = 0u;
-      const uint32_t multi = rowmask & ~single;
       if (multi) {
         const uint32_t wreal = wstart & rowmask;
         const uint32_t starts = wreal | 1u;                // the segment entering from below starts at row 0
@@ -989,9 +1033,8 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
         const uint32_t cross_mask = ent_mask | lea_mask;
 
         // (1b) rows whose sample differs from the row below, then the rows of non-constant segments
-        uint32_t breaks = 0u;
-        {
-          uint32_t at = ln.f + (uint32_t)i0 * ROW;
+        if (!have_breaks) {
+          const uint32_t at = ln.f + (uint32_t)i0 * ROW;
           float prev = lds_f32(at);
           if (rows == 32) {
 #pragma unroll
