@@ -831,6 +831,11 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
   // Variants with registers to spare (2 CTAs per SM, or one wide CTA) step a 64-bit label pointer
   // and share one pass over the samples between (1a) and (1b); at 40 registers both cost spills.
   constexpr bool kRoomy = Wide || MinCtas == 2;
+  // One CTA per SM (lines of more than 512 rows): nothing else on the SM hides the label-load
+  // latency, so the warps are decoupled -- one early barrier, then every warp loads its labels,
+  // waits for the float tile and finishes its chunks at its own pace (1024^3: -7 %).  With two or
+  // three CTAs per SM the other CTAs hide it and the extra work per chunk only costs.
+  constexpr bool kDecoupled = Wide;
   constexpr uint32_t ROW = TX * 4;                    // bytes between rows of fs / between words
 
   const int n = g.n;
@@ -867,23 +872,38 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
 
   pdl_launch_dependents();             // the next pass may start staging its labels during our tail
   if (!UseTMA) pdl_wait_for_previous_grid();           // plain loads of f happen in the staging loop
+  // Float tile by TMA, border-term table, chunk mask.  (kDecoupled) together with the mbarrier the
+  // table and the mask are the only things a warp needs from other warps before the votes at the end
+  // of stage 1, so the one barrier comes here, early, while no warp has loads in flight yet; the tile
+  // is requested right behind it, together with the first label loads (measured: better than ahead of it).
   if (UseTMA && threadIdx.x == 0) {
-    pdl_wait_for_previous_grid();      // f is complete only when the previous pass has finished
+    if (!kDecoupled) pdl_wait_for_previous_grid();      // f is complete only when the previous pass has finished
     mbar_init(bar, 1);
-    mbar_expect_tx(bar, (unsigned)rows_alloc * ROW);
-    for (int bx = 0; bx < tb.nboxes; ++bx)
-      tma_load_3d(smem_tile + (size_t)bx * tb.box_rows * ROW, &fmap, (int)inner0, bx * tb.box_rows, (int)outer, bar);
+    if (!kDecoupled) {
+      mbar_expect_tx(bar, (unsigned)rows_alloc * ROW);
+      for (int bx = 0; bx < tb.nboxes; ++bx)
+        tma_load_3d(smem_tile + (size_t)bx * tb.box_rows * ROW, &fmap, (int)inner0, bx * tb.box_rows, (int)outer, bar);
+    }
   }
-
-  // ============ stage 0: labels -> run-start / background words; border-term table ============
   if (threadIdx.x < TX) sts_u32(nz_a + threadIdx.x * 4u, 0u);
   for (int i = threadIdx.x; i < n + 2; i += blockDim.x) {
     const float e = (float)i;
     sts_f32(sq_a + (uint32_t)i * 4u, __fmul_rn(w2, __fmul_rn(e, e)));
   }
+  if (kDecoupled) {
+    __syncthreads();
+    if (UseTMA && threadIdx.x == 0) {
+      pdl_wait_for_previous_grid();
+      mbar_expect_tx(bar, (unsigned)rows_alloc * ROW);
+      for (int bx = 0; bx < tb.nboxes; ++bx)
+        tma_load_3d(smem_tile + (size_t)bx * tb.box_rows * ROW, &fmap, (int)inner0, bx * tb.box_rows, (int)outer, bar);
+    }
+  }
+
+  // ============ stage 0: labels -> run-start / background words ============
   for (int c = chunk0; c < nchunks; c += chunk_step) {
     const int i0 = c << 5;
-    uint32_t wstart = 0, wzero = 0;
+    uint32_t wstart = 0, wzero = 0, ext = 1u;      // ext: a run starts at row i0 + 32 (or the line ends there)
     if (live) {
       uint32_t idx = (uint32_t)i0 * ls + (uint32_t)x;
       const LT* lp = tl + idx;               // (kRoomy) stepped by one line stride per row
@@ -900,6 +920,7 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
           if (Epilogue && here == 0) wzero |= (1u << r);
           prev = here;
         }
+        if (kDecoupled && i0 + 32 < n) ext = (kRoomy ? *lp : tl[idx]) != prev;
       } else {
         for (int r = 0; r < n - i0; ++r) {
           const LT here = kRoomy ? *lp : tl[idx];
@@ -916,9 +937,10 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
     }
     sts_u32(startw_a + (uint32_t)c * ROW + (uint32_t)x * 4u, wstart);
     if (Epilogue) sts_u32(zerow_a + (uint32_t)c * ROW + (uint32_t)x * 4u, wzero);
+    if (kDecoupled) sts_u8(cflag_a + (uint32_t)(c * TX + x), ext << 2);   // bit 2 of the chunk's flag byte, for stage 1
   }
   pdl_wait_for_previous_grid();        // nobody may store into f before the previous pass is done
-  __syncthreads();         // words, table (and plain-loaded tile) visible; orders the mbarrier init
+  if (!UseTMA || !kDecoupled) __syncthreads();   // words, table (and plain-loaded tile) visible; orders the mbarrier init
   if (UseTMA) mbar_wait(bar, 0);       // float tile has landed
 
   // every shared address used from here on carries the token, so no (non-volatile) load of the
@@ -954,8 +976,10 @@ later_axis_tile_kernel(const __grid_constant__ CUtensorMap fmap,
       const uint32_t wstart = lds_u32(startcol + (uint32_t)c * ROW);
       const uint32_t wzero = Epilogue ? lds_u32(zerocol + (uint32_t)c * ROW) : 0u;
       // bit r of `nextw`: a run starts at row i0 + r + 1 (the line end counts as a start)
+      // ext: a run starts at row i0 + 32 (the line end counts as a start)
       uint32_t ext = 1u;
-      if (i0 + 32 < n) ext = lds_u32(startcol + (uint32_t)(c + 1) * ROW) & 1u;
+      if (kDecoupled) ext = (lds_u8_volatile(cflagcol + (uint32_t)c * TX) >> 2) & 1u;     // (this thread's own store)
+      else if (i0 + 32 < n) ext = lds_u32(startcol + (uint32_t)(c + 1) * ROW) & 1u;
       const uint32_t nextw = (wstart >> 1) | (ext << 31);
       uint32_t single = wstart & nextw & rowmask;          // runs of length one
       if (!border_lo && c == 0) single &= ~1u;             // rows lacking a border term go the long way
