@@ -143,6 +143,8 @@ int edtb200_transform_voxel_graph(const void *labels, int label_bytes, const uns
  *     in that pass's store (sqrt, negate background) -- use them on the last pass only.
  *     border_lo / border_hi say independently whether the low / high end of the axis is a
  *     volume face with black_border (an interior slab face is neither).
+ *     pass_later works IN PLACE on f_dev (input = the previous pass's output) and only writes
+ *     the elements whose value it changes.
  */
 int edtb200_pass_first(const void *labels_dev, int label_bytes,
                        int64_t sx, int64_t sy, int64_t sz, float wx,

@@ -82,6 +82,37 @@ def test_cfg2_full_volume_live(edt, reference):
   assert_same(edt.edtsq(lab, anisotropy=(1, 1, 1)), want, "cfg2 512^3")
 
 
+def test_wide_lines_and_rows_that_are_not_stored(edt, oracle, reference):
+  """Lines of 513..1024 rows (one wide CTA per SM, decoupled warps, chunk mask) and the rows the later
+  passes do not store because they keep their value (the passes work in place): solid volumes with
+  and without a border through every epilogue, label noise (every row of Y / Z unchanged), blocks."""
+  ref = checker(reference, oracle)
+  rng = np.random.default_rng(31)
+  wide = np.ones((24, 1024, 16), dtype=np.uint8, order="F")
+  for fn in ("edtsq", "edt", "sdf"):
+    for bb in (False, True):
+      assert_same(getattr(edt, fn)(wide, anisotropy=(6, 6, 30), black_border=bb),
+                  ref(fn, wide, anisotropy=(6, 6, 30), black_border=bb), ("wide ones", fn, bb))
+  wide[11, 700, 5] = 0
+  wide[3, 64:96, :] = 7                                     # a chunk-aligned slab of another label
+  assert_same(edt.edt(wide, anisotropy=(1, 2, 1)), ref("edt", wide, anisotropy=(1, 2, 1)), "wide hole")
+  for n in (1000, 1024, 513):
+    noise = np.asfortranarray(rng.integers(0, 200, (20, n, 12), dtype=np.uint32))
+    for _ in range(2):                                      # the second call takes the label-noise variant
+      got = edt.edtsq(noise, black_border=True)
+    assert_same(got, ref("edtsq", noise, black_border=True), ("wide noise", n))
+    blocks = np.asfortranarray(np.repeat(np.repeat(rng.integers(1, 5, (3, (n + 31) // 32, 2), dtype=np.uint16), 8, 0),
+                                         32, 1)[:, :n].repeat(8, 2))
+    assert_same(edt.sdf(blocks, anisotropy=(2, 1, 3)), ref("sdf", blocks, anisotropy=(2, 1, 3)), ("wide blocks", n))
+  # 512-row lines (three CTAs per SM): solid two-label volume, every function
+  solid = np.ones((40, 512, 36), dtype=np.uint16, order="F")
+  solid[:, :, 18:] = 2
+  solid[:, 300:, :9] = 0
+  for fn in ("edtsq", "edt", "sdfsq", "sdf"):
+    assert_same(getattr(edt, fn)(solid, anisotropy=(2, 1, 3), black_border=True),
+                ref(fn, solid, anisotropy=(2, 1, 3), black_border=True), ("solid", fn))
+
+
 # ---- per-label views ------------------------------------------------------------------
 
 def many_labels(shape, nlabels, seed, dtype=np.uint32):

@@ -61,6 +61,21 @@ grid = np.stack(np.meshgrid(np.arange(40.0), np.arange(512.0), np.arange(24.0), 
 vor = np.asfortranarray((cKDTree(pts).query(grid)[1] + 1).astype(np.uint16).reshape(40, 512, 24))
 check("voronoi int", edt.edtsq(vor, anisotropy=(1, 1, 2)), oracle.edtsq(vor, anisotropy=(1, 1, 2)))
 check("voronoi double", edt.edtsq(vor, anisotropy=(0.7, 1.3, 2.9)), oracle.edtsq(vor, anisotropy=(0.7, 1.3, 2.9)))
+# wide variant (lines of 513..1024 rows: decoupled warps, chunk mask) and the constant runs that are
+# not stored: solid volume with a black border through every epilogue, blocks, noise, one hole
+wide = np.ones((16, 1024, 8), dtype=np.uint8, order="F")
+check("wide ones bb", edt.edtsq(wide, anisotropy=(6, 6, 30), black_border=True),
+      oracle.edtsq(wide, anisotropy=(6, 6, 30), black_border=True))
+check("wide ones sdf", edt.sdf(wide, black_border=True), oracle.sdf(wide, black_border=True))
+wide[7, 600, 3] = 0
+check("wide hole", edt.edt(wide), oracle.edt(wide))
+for kind in ("iid", "blocks"):
+  lab = np.asfortranarray(cases.random_volume(rng, (16, 1000, 12), kind, np.uint32))
+  check("wide " + kind, edt.edtsq(lab, black_border=(kind == "blocks")), oracle.edtsq(lab, black_border=(kind == "blocks")))
+solid = np.ones((48, 96, 40), dtype=np.uint16, order="F")
+solid[:, :, 20:] = 2
+check("solid edt", edt.edt(solid, anisotropy=(2, 1, 3), black_border=True),
+      oracle.edt(solid, anisotropy=(2, 1, 3), black_border=True))
 # per-label statistics and box-restricted extraction
 import torch  # noqa: E402
 lt = torch.from_numpy(np.ascontiguousarray(vor.astype(np.int32))).cuda()
