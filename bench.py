@@ -489,8 +489,7 @@ def ours(args):
 
   peak, peak_src = measured_peak_gbs()
   if world > 1:
-    # the exchange dominates: report the whole step against HBM for orientation only
-    alg = (3 * LABEL_BYTES + 20) * nvox
+    # whole step against HBM for orientation (bytes that have to move, see rows_changed; set below)
     # dominant kernel: the Z pass of this rank's slab, timed by the library's per-pass events over the
     # K steps that followed the timed region (rank 0's slab; every rank runs the same kernels)
     zms = None
@@ -504,7 +503,9 @@ def ours(args):
     except Exception:
       zms = None
     # labels + distances read + 4 B per voxel the pass changes (rows that keep their value are not stored)
-    zalg = (LABEL_BYTES + 4) * nvox + 4 * rows_changed(labels_dev, (ANISOTROPY[2], ANISOTROPY[1], ANISOTROPY[0]), False)[1]
+    cy, cz = rows_changed(labels_dev, (ANISOTROPY[2], ANISOTROPY[1], ANISOTROPY[0]), False)
+    zalg = (LABEL_BYTES + 4) * nvox + 4 * cz
+    alg = 3 * (LABEL_BYTES + 4) * nvox + 4 * (cy + cz)
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "kernel": "later_axis_tile_kernel<4,32,false,true,false,2,true> (Z pass of one slab)",
                 "achieved": (zalg / (zms * 1e-3) / 1e9) if zms else None, "peak": peak, "unit": "GB/s",
