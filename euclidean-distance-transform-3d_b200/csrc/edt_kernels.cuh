@@ -260,7 +260,7 @@ template <> struct Vec4Labels<8> {
 // Plain = true: squared EDT, background forced to 0, no sqrt / sign (the hot configuration);
 // Plain = false: behaviour selected by `flags` at run time.
 template <int Bytes, int K, bool Plain>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, K >= 8 ? 3 : 1)      // 1024-voxel rows: 99 registers uncapped, 2 CTAs per SM
 first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
                       float* __restrict__ out, int64_t nlines, int sx,
                       const float* __restrict__ table, int border, int flags, RunStat stat) {

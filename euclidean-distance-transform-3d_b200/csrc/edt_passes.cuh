@@ -29,7 +29,7 @@ int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float
       reinterpret_cast<uintptr_t>(f) % 16 == 0) {
     const size_t smem = sizeof(float) * (size_t)(sx + 2);
     int64_t blocks = (nlines + 7) / 8;
-    const int64_t cap = (int64_t)dc.sm_count * 8;
+    const int64_t cap = (int64_t)dc.sm_count * (sx > 512 ? 12 : 8);   // whole waves at 4 (rows <= 512) / 3 CTAs per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const LT* lab = static_cast<const LT*>(labels);
