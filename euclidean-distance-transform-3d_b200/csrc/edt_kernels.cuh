@@ -260,7 +260,10 @@ template <> struct Vec4Labels<8> {
 // Plain = true: squared EDT, background forced to 0, no sqrt / sign (the hot configuration);
 // Plain = false: behaviour selected by `flags` at run time.
 template <int Bytes, int K, bool Plain>
-__global__ void __launch_bounds__(256, K >= 8 ? 3 : 1)      // 1024-voxel rows: 99 registers uncapped, 2 CTAs per SM
+// Registers capped for occupancy: uncapped the kernel takes 64 (rows <= 512: 4 CTAs per SM) / 99 registers
+// (1024-voxel rows: 2 CTAs); at 48 / 80 it still has no spills and runs 5 / 3 CTAs per SM
+// (measured: headline 0.585 -> 0.564 ms, 1024^3 5.21 -> 4.97 ms; 6 CTAs at 40 registers spill: 0.573).
+__global__ void __launch_bounds__(256, K >= 8 ? 3 : 5)
 first_axis_vec_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels,
                       float* __restrict__ out, int64_t nlines, int sx,
                       const float* __restrict__ table, int border, int flags, RunStat stat) {

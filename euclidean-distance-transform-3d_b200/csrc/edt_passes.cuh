@@ -29,7 +29,8 @@ int launch_first(const void* labels, float* f, int64_t nlines, int64_t sx, float
       reinterpret_cast<uintptr_t>(f) % 16 == 0) {
     const size_t smem = sizeof(float) * (size_t)(sx + 2);
     int64_t blocks = (nlines + 7) / 8;
-    const int64_t cap = (int64_t)dc.sm_count * (sx > 512 ? 12 : 8);   // whole waves at 4 (rows <= 512) / 3 CTAs per SM
+    static const int xgrid = getenv("EDTB200_X_GRID") ? atoi(getenv("EDTB200_X_GRID")) : 0;     // A/B switch
+    const int64_t cap = (int64_t)dc.sm_count * (xgrid ? xgrid : (sx > 512 ? 12 : 15));   // whole waves at 5 (rows <= 512) / 3 CTAs per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const LT* lab = static_cast<const LT*>(labels);
