@@ -83,6 +83,8 @@ def _lib():
   lib.edtb200_pass_first.restype = ci
   lib.edtb200_pass_later.argtypes = [vp, ci, ci, i64, i64, i64, f32, ci, ci, ci, vp, ci, vp]
   lib.edtb200_pass_later.restype = ci
+  lib.edtb200_slab_pack.argtypes = [vp, vp, i64, i64, i64, ci, ctypes.POINTER(ctypes.c_int64), ci, ci, vp]
+  lib.edtb200_slab_pack.restype = ci
   lib.edtb200_slab_face_runs.argtypes = [vp, ci, i64, i64, i64, ci, ci, ci, vp, vp, ci, vp]
   lib.edtb200_slab_face_runs.restype = ci
   lib.edtb200_slab_face_fixup.argtypes = [vp, ci, i64, i64, i64, ci, ci, f32, ci, vp, vp, vp, vp, vp, ci, vp]

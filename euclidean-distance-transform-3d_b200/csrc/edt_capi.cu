@@ -893,6 +893,38 @@ int edtb200_slab_face_runs(const void* labels_dev, int label_bytes, int64_t sx, 
   return 0;
 }
 
+int edtb200_slab_pack(const void* src_dev, void* dst_dev, int64_t zc, int64_t sy, int64_t row_bytes, int parts,
+                      const int64_t* y_start, int unpack, int device, void* stream_v) {
+  if (zc < 0 || sy < 0 || row_bytes < 0) return fail(EDTB200_EINVAL, "negative extent");
+  if (parts < 1 || parts > 64) return fail(EDTB200_EINVAL, "parts must be in 1..64");
+  if (!y_start) return fail(EDTB200_EINVAL, "null pointer");
+  edtb200::SlabParts sp;
+  sp.n = parts;
+  for (int i = 0; i <= parts; ++i) {
+    sp.start[i] = y_start[i];
+    if ((i == 0 && y_start[i] != 0) || (i > 0 && y_start[i] < y_start[i - 1]))
+      return fail(EDTB200_EINVAL, "y_start must rise from 0 to sy");
+  }
+  if (y_start[parts] != sy) return fail(EDTB200_EINVAL, "y_start must rise from 0 to sy");
+  if (zc * sy * row_bytes == 0) return 0;
+  if (!src_dev || !dst_dev) return fail(EDTB200_EINVAL, "null pointer");
+  DeviceGuard restore_device;
+  DeviceCache* dc = nullptr;
+  int rc = probe(device, &dc);
+  if (rc) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int vec16 = (row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(src_dev) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(dst_dev) % 16 == 0) ? 1 : 0;
+  const int64_t rows = zc * sy;
+  const unsigned blocks = (unsigned)std::min<int64_t>(rows, (int64_t)dc->sm_count * 32);
+  const unsigned char* a = static_cast<const unsigned char*>(src_dev);
+  unsigned char* b = static_cast<unsigned char*>(dst_dev);
+  if (unpack) edtb200::slab_pack_kernel<true><<<blocks, 256, 0, stream>>>(a, b, zc, sy, row_bytes, vec16, sp);
+  else edtb200::slab_pack_kernel<false><<<blocks, 256, 0, stream>>>(a, b, zc, sy, row_bytes, vec16, sp);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int edtb200_slab_face_fixup(const void* labels_dev, int label_bytes, int64_t sx, int64_t sy, int64_t sz,
                             int high_face, int halo, float wz, int flags, const void* nb_label_dev,
                             const unsigned char* nb_m_dev, const float* nb_f_dev, float* f_dev, int* inexact_dev,

@@ -192,4 +192,36 @@ slab_fixup_kernel(const typename LabelOf<Bytes>::type* __restrict__ labels, floa
   }
 }
 
+// ---- Z slabs <-> Y slabs (the transposition fallback of the slab split) ----
+// A rank's slab (zc, sy, row) is cut along y into `n` parts (part i = rows start[i] .. start[i+1]);
+// packed, part i is one contiguous block (zc, c_i, row) -- what rank i receives in ONE message --
+// and the blocks follow one another in rank order.  ONE launch moves the whole slab either way
+// (Unpack = the inverse map, for the way back), 16 bytes per thread and access when the rows allow.
+struct SlabParts {
+  int n;
+  long long start[65];       // start[n] = sy
+};
+
+template <bool Unpack>
+__global__ void __launch_bounds__(256)
+slab_pack_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, long long zc, long long sy,
+                 long long rowbytes, int vec16, SlabParts parts) {
+  const long long rows = zc * sy;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const long long z = row / sy, y = row - z * sy;
+    int i = 0;
+    while (i + 1 < parts.n && y >= parts.start[i + 1]) ++i;
+    const long long s = parts.start[i], c = parts.start[i + 1] - s;
+    const long long packed = (zc * s + z * c + (y - s)) * rowbytes, plain = row * rowbytes;
+    const unsigned char* a = src + (Unpack ? packed : plain);
+    unsigned char* b = dst + (Unpack ? plain : packed);
+    if (vec16) {
+      for (long long k = (long long)threadIdx.x * 16; k < rowbytes; k += (long long)blockDim.x * 16)
+        *reinterpret_cast<uint4*>(b + k) = *reinterpret_cast<const uint4*>(a + k);
+    } else {
+      for (long long k = threadIdx.x; k < rowbytes; k += blockDim.x) b[k] = a[k];
+    }
+  }
+}
+
 }  // namespace edtb200

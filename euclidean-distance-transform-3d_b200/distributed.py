@@ -100,6 +100,17 @@ class CudaPasses:
                                            ctypes.c_void_p(sym_hi or None), ctypes.c_uint64(step),
                                            status.data_ptr(), self.device.index, self._stream()))
 
+  def repartition(self, src, dst, ysplit, unpack=False):
+    """Z slab (zc, sy, row) <-> the exchange layout of the transposition fallback, ONE launch
+    (csrc/edt_slab.cuh: slab_pack_kernel).  `src` / `dst` are contiguous tensors of equal byte size
+    whose slab side has shape (zc, sy, row); ysplit = [(y_start, y_count)] per rank."""
+    slab = dst if unpack else src
+    zc, sy = slab.shape[0], slab.shape[1]
+    row_bytes = slab.shape[2] * slab.element_size()
+    starts = (ctypes.c_int64 * (len(ysplit) + 1))(*([s for s, _ in ysplit] + [sy]))
+    self._check(self.lib.edtb200_slab_pack(src.data_ptr(), dst.data_ptr(), zc, sy, row_bytes, len(ysplit), starts,
+                                           1 if unpack else 0, self.device.index, self._stream()))
+
   def face_runs(self, labels, high_face, halo, signed, overflow, out=None):
     """uint8 (sy, sx) run lengths at one face; raises the device int `overflow` when too long."""
     sz, sy, sx = labels.shape
@@ -122,12 +133,14 @@ class CudaPasses:
                                                  inexact.data_ptr(), self.device.index, self._stream()))
 
 
-def _all_to_all(send_chunks, recv_chunks, group):
+def _all_to_all(send_chunks, recv_chunks, group, peers=None):
   """Exchange send_chunks[j] -> rank j / recv_chunks[i] <- rank i (contiguous tensors; the own
-  chunk is copied locally).  Empty chunks are skipped on both sides (sizes are symmetric)."""
+  chunk is copied locally).  Empty chunks are skipped on both sides (sizes are symmetric).
+  `peers` names the rank of every chunk pair when several arrays travel in one grouped exchange
+  (every rank lists its chunks in the same order, so sends and receives match up pair by pair)."""
   rank = dist.get_rank(group)
   ops = []
-  for peer, (s, r) in enumerate(zip(send_chunks, recv_chunks)):
+  for peer, (s, r) in zip(peers if peers is not None else range(len(send_chunks)), zip(send_chunks, recv_chunks)):
     if peer == rank:
       r.copy_(s)
       continue
@@ -439,15 +452,28 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
   else:
     lab_bytes = torch.empty((0, sy, sx * esz), dtype=torch.uint8, device=labels_local.device)
 
-  f_send = [f[:, s:s + c, :].contiguous() for (s, c) in ysplit]
-  l_send = [lab_bytes[:, s:s + c, :].contiguous() for (s, c) in ysplit]
   f_cols = passes.empty_f32((sz, yc, sx))
   l_cols = torch.empty((sz, yc, sx * esz), dtype=torch.uint8, device=labels_local.device)
   zoff = [sum(depths[:i]) for i in range(world)]
   f_recv = [f_cols[zoff[i]:zoff[i] + depths[i]] for i in range(world)]
   l_recv = [l_cols[zoff[i]:zoff[i] + depths[i]] for i in range(world)]
-  _all_to_all(f_send, f_recv, group)
-  _all_to_all(l_send, l_recv, group)
+  packed = hasattr(passes, "repartition") and world <= 64
+  if packed:
+    # one launch per array packs the slab into per-rank blocks; distances and labels travel in ONE
+    # grouped exchange and land in place (contiguous z ranges of the column arrays)
+    f_stage = passes.empty_f32((zc * sy * sx,))
+    l_stage = torch.empty((zc * sy * sx * esz,), dtype=torch.uint8, device=labels_local.device)
+    if zc:
+      passes.repartition(f, f_stage, ysplit)
+      passes.repartition(lab_bytes, l_stage, ysplit)
+    f_send = [f_stage[zc * s * sx:zc * (s + c) * sx].view(zc, c, sx) for (s, c) in ysplit]
+    l_send = [l_stage[zc * s * sx * esz:zc * (s + c) * sx * esz].view(zc, c, sx * esz) for (s, c) in ysplit]
+    _all_to_all(f_send + l_send, f_recv + l_recv, group, peers=list(range(world)) * 2)
+  else:
+    f_send = [f[:, s:s + c, :].contiguous() for (s, c) in ysplit]
+    l_send = [lab_bytes[:, s:s + c, :].contiguous() for (s, c) in ysplit]
+    _all_to_all(f_send, f_recv, group)
+    _all_to_all(l_send, l_recv, group)
 
   if yc and sz:
     labels_cols = l_cols.view(labels_local.dtype).reshape(sz, yc, sx)
@@ -455,6 +481,12 @@ def slab_transform(labels_local, anisotropy=(1.0, 1.0, 1.0), black_border=False,
 
   out = passes.empty_f32((zc, sy, sx))
   back_send = [f_cols[zoff[i]:zoff[i] + depths[i]] for i in range(world)]          # contiguous z ranges
+  if packed:
+    back_recv = f_send                                       # the staging blocks are free again
+    _all_to_all(back_send, back_recv, group)
+    if zc:
+      passes.repartition(f_stage, out, ysplit, unpack=True)
+    return out
   back_recv = [passes.empty_f32((zc, c, sx)) for (_, c) in ysplit]
   _all_to_all(back_send, back_recv, group)
   for (s, c), chunk in zip(ysplit, back_recv):

@@ -186,6 +186,20 @@ int edtb200_slab_face_fixup(const void *labels_dev, int label_bytes,
                             const float *nb_f_dev, float *f_dev, int *inexact_dev,
                             int device, void *stream);
 
+/* Exact fallback of the Z-slab decomposition (runs deeper than any halo): the ranks re-partition
+ * the volume from Z slabs to Y slabs, run the third-axis pass on whole z-lines and re-partition
+ * back.  edtb200_slab_pack moves a device-resident slab (zc, sy, row_bytes) -- distances or
+ * labels, the row is opaque bytes -- into the exchange layout in ONE launch: the slab is cut
+ * along y into `parts` pieces (piece i = rows y_start[i] .. y_start[i+1], y_start[0] = 0,
+ * y_start[parts] = sy; HOST array of parts + 1 entries, parts <= 64), and piece i becomes one
+ * contiguous block (zc, c_i, row_bytes), the blocks in piece order -- block i is the single
+ * message for rank i.  unpack != 0 applies the inverse map (blocks -> slab) for the way back.
+ * Replaces what the reference gets from having the whole volume in one address space
+ * (src/edt.hpp:450-475).
+ */
+int edtb200_slab_pack(const void *src_dev, void *dst_dev, int64_t zc, int64_t sy, int64_t row_bytes,
+                      int parts, const int64_t *y_start, int unpack, int device, void *stream);
+
 /* One whole step of the Z-slab decomposition on this rank, device-resident, asynchronous on
  * `stream`: X pass, Y pass, publication of this slab's faces to the neighbours, Z pass (interior
  * faces open) and the fix-up that folds the neighbours' rows in -- five launches from ONE call, no

@@ -22,10 +22,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 class OraclePasses:
   """Stand-in for CudaPasses: same interface, numpy arithmetic from oracle/ (tests only)."""
 
-  def __init__(self):
+  def __init__(self, packed=True):
     from oracle import oracle
     self.oracle = oracle
     self.signed = False
+    if not packed:                  # hide `repartition`: the transposition then slices and concatenates
+      self.repartition = None
+
+  def __getattribute__(self, name):
+    value = object.__getattribute__(self, name)
+    if name == "repartition" and value is None:
+      raise AttributeError(name)
+    return value
 
   def empty_f32(self, shape):
     return torch.zeros(shape, dtype=torch.float32)
@@ -50,6 +58,18 @@ class OraclePasses:
     if negate:
       arr[zero] *= -1.0
 
+
+  # torch restatement of slab_pack_kernel (edt_slab.cuh): slab (zc, sy, row) <-> per-rank blocks
+  def repartition(self, src, dst, ysplit, unpack=False):
+    slab = dst if unpack else src
+    zc, sy, row = slab.shape
+    flat = (src if unpack else dst).reshape(-1)
+    for s, c in ysplit:
+      block = flat[zc * s * row:zc * (s + c) * row].view(zc, c, row)
+      if unpack:
+        dst[:, s:s + c, :] = block
+      else:
+        block.copy_(src[:, s:s + c, :])
 
   # numpy restatement of the two slab-face kernels (edt_kernels.cuh: face_runs_kernel, face_fixup_kernel)
   def face_runs(self, labels, high_face, halo, signed, overflow, out=None):
@@ -165,8 +185,9 @@ def _worker_body(rank, world, queue):
       local = torch.from_numpy(vol[z0:z0 + zc].copy())
       for halo in (2, 64):            # 2: the halo method where it is exact; 64: always the transpose
         info = {}
-        out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed, passes=OraclePasses(), halo=halo,
-                                info=info)
+        # (odd cases take the transposition without the packed exchange layout)
+        out = ed.slab_transform(local, an, bb, sqrt=sqrt, signed=signed, passes=OraclePasses(packed=idx % 2 == 0),
+                                halo=halo, info=info)
         queue.put((idx, halo, info["method"], rank, z0, out.numpy()))
 
 
@@ -308,6 +329,29 @@ def test_deferred_verdicts_are_combined_once_per_batch():
       if it[0] == idx:
         got[it[2]:it[2] + it[3].shape[0]] = it[3]
     assert np.array_equal(got, fn(_volume(CASES[idx]), anisotropy=an, black_border=bb), equal_nan=True), idx
+
+
+@pytest.mark.gpu
+def test_slab_pack_kernel_against_slicing():
+  """edtb200_slab_pack (one launch, either direction) == slicing the slab per rank and concatenating."""
+  sys.path.insert(0, ROOT)
+  import edt_b200.distributed as ed
+  dev = torch.device("cuda", 0)
+  passes = ed.CudaPasses(dev)
+  gen = torch.Generator(device="cpu").manual_seed(5)
+  for zc, sy, sx, dtype, world in ((7, 20, 64, torch.float32, 3), (5, 9, 33, torch.uint8, 4), (3, 8, 10, torch.int16, 8),
+                                   (4, 512, 128, torch.float32, 8), (0, 6, 4, torch.float32, 2), (6, 5, 12, torch.int64, 7)):
+    ysplit = ed.split_extent(sy, world)                      # world > sy: some parts are empty
+    src = torch.randint(0, 120, (zc, sy, sx), generator=gen).to(dtype).to(dev)
+    packed = torch.empty(src.numel(), dtype=dtype, device=dev)
+    passes.repartition(src, packed, ysplit)
+    want = torch.cat([src[:, s:s + c, :].reshape(-1) for s, c in ysplit]) if src.numel() else packed
+    assert torch.equal(packed, want), (zc, sy, sx, dtype, world)
+    back = torch.full_like(src, 99)
+    passes.repartition(packed, back, ysplit, unpack=True)
+    assert torch.equal(back, src), (zc, sy, sx, dtype, world, "unpack")
+  with pytest.raises(ed.EDTError):
+    passes.repartition(torch.zeros((2, 4, 4), device=dev), torch.zeros(32, device=dev), [(0, 2), (3, 1)])   # gap
 
 
 def test_split_extent():
