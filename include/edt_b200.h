@@ -29,7 +29,10 @@
 extern "C" {
 #endif
 
-#define EDTB200_VERSION 100
+/* 100: round 1 (transform, per-axis passes, slab face kernels).  200: additions only --
+ * edtb200_transform_multi, edtb200_slab_step / _stage_bytes / _pack, edtb200_label_stats / _extract,
+ * edtb200_host_alloc / _free; every 100-level entry point keeps its signature and meaning. */
+#define EDTB200_VERSION 200
 
 /* flags */
 #define EDTB200_SQRT             1  /* emit sqrt(edtsq): reference _edt3d (src/edt.hpp:591-604) /
